@@ -1,0 +1,151 @@
+// probe_sweep.cu — standalone tuning harness for the hbm_probe kernel variants.
+// Not part of the product path: it instantiates the kernels in hbm_probe.cuh
+// over a grid of launch shapes, times each with CUDA events (3 warm-ups, K
+// timed launches, inputs 1 GiB >> 126 MB L2) and checks checksum/mismatches
+// against the closed-form CPU value. Output: CSV on stdout.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
+//        -I k8s-device-plugin_b200/csrc tools/probe_sweep.cu -o tools/probe_sweep
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "hbm_probe.cuh"
+
+using namespace b2dp;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); exit(2); } } while (0)
+
+static unsigned long long cpu_checksum(unsigned long long n_words, uint32_t seed) {
+    unsigned long long s = 0;
+    for (unsigned long long i = 0; i < n_words; ++i) s += (uint32_t)((uint32_t)i * kPatternMul) ^ seed;
+    return s;
+}
+
+struct Bufs {
+    uint4 *a, *b; unsigned long long n_vec; ProbeCtl* ctl; ProbeOut* out_h; ProbeOut* out_d;
+    uint32_t seed; int cur;  // cur: which buffer holds pattern(seed)
+};
+
+using LaunchFn = void (*)(const uint4*, uint4*, unsigned long long, uint32_t, uint32_t, ProbeCtl*, ProbeOut*,
+                          unsigned long long, int grid, cudaStream_t);
+
+template <int T, int U> static void launch_r128(const uint4* s, uint4* d, unsigned long long n, uint32_t seed,
+    uint32_t delta, ProbeCtl* c, ProbeOut* o, unsigned long long seq, int grid, cudaStream_t st) {
+    hbm_probe_r128<T, U><<<grid, T, 0, st>>>(s, d, n, seed, delta, c, o, seq);
+}
+template <int T, int U> static void launch_r256(const uint4* s, uint4* d, unsigned long long n, uint32_t seed,
+    uint32_t delta, ProbeCtl* c, ProbeOut* o, unsigned long long seq, int grid, cudaStream_t st) {
+    hbm_probe_r256<T, U><<<grid, T, 0, st>>>(s, d, n, seed, delta, c, o, seq);
+}
+template <int CW, int TV, int ST> static void launch_tma(const uint4* s, uint4* d, unsigned long long n, uint32_t seed,
+    uint32_t delta, ProbeCtl* c, ProbeOut* o, unsigned long long seq, int grid, cudaStream_t st) {
+    constexpr size_t smem = (size_t)ST * TV * 16 + 2 * ST * 8;
+    static bool once = false;
+    if (!once) { CK(cudaFuncSetAttribute(hbm_probe_tma<CW, TV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
+    hbm_probe_tma<CW, TV, ST><<<grid, (CW + 1) * 32, smem, st>>>(s, d, n, seed, delta, c, o, seq);
+}
+
+__global__ void plain_copy(const uint4* __restrict__ s, uint4* __restrict__ d, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+struct Cfg { std::string name; LaunchFn fn; int ctas_per_sm; };
+
+int main(int argc, char** argv) {
+    unsigned long long bytes = 1ull << 30;
+    int iters = 10, warm = 3;
+    const char* only = nullptr;
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "--bytes")) bytes = strtoull(argv[++i], 0, 0);
+        else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--only")) only = argv[++i];
+    }
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    fprintf(stderr, "# %s, %d SMs, bytes=%llu\n", prop.name, sms, bytes);
+
+    Bufs B{}; B.n_vec = bytes / 16;
+    CK(cudaMalloc(&B.a, bytes)); CK(cudaMalloc(&B.b, bytes));
+    CK(cudaMalloc(&B.ctl, sizeof(ProbeCtl)));
+    ProbeCtl init{}; init.first_bad = ~0ull; init.t_start_ns = ~0ull;
+    CK(cudaMemcpy(B.ctl, &init, sizeof init, cudaMemcpyHostToDevice));
+    CK(cudaHostAlloc(&B.out_h, sizeof(ProbeOut), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&B.out_d, B.out_h, 0));
+    cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+
+    B.seed = 0x5EED0000u; B.cur = 0;
+    hbm_fill<256><<<sms * 8, 256, 0, st>>>(B.a, B.n_vec, B.seed);
+    CK(cudaStreamSynchronize(st));
+
+    std::vector<Cfg> cfgs;
+#define R128(T, U) for (int k : {1, 2, 4, 8, 16}) if (k * T <= 2048) cfgs.push_back({"r128_t" #T "_u" #U, launch_r128<T, U>, k});
+#define R256(T, U) for (int k : {1, 2, 4, 8}) if (k * T <= 2048) cfgs.push_back({"r256_t" #T "_u" #U, launch_r256<T, U>, k});
+#define TMA(CW, TV, ST) for (int k : {1, 2, 3, 4, 6}) if ((size_t)k * ((size_t)ST * TV * 16 + 1024) <= 227 * 1024 && k * (CW + 1) * 32 <= 2048) \
+        cfgs.push_back({"tma_cw" #CW "_tv" #TV "_st" #ST, launch_tma<CW, TV, ST>, k});
+    R128(256, 2) R128(256, 4) R128(256, 8) R128(512, 2) R128(512, 4) R128(512, 8) R128(1024, 2) R128(1024, 4)
+    R256(256, 1) R256(256, 2) R256(256, 4) R256(512, 1) R256(512, 2) R256(512, 4)
+    TMA(4, 512, 4) TMA(4, 1024, 3) TMA(4, 1024, 4) TMA(4, 1024, 6) TMA(4, 2048, 3) TMA(4, 2048, 4)
+    TMA(8, 1024, 4) TMA(8, 2048, 3) TMA(8, 2048, 4) TMA(8, 4096, 3) TMA(2, 1024, 4) TMA(2, 512, 6)
+
+    // baselines: driver D2D memcpy and a plain copy kernel (no verify)
+    auto time_it = [&](auto&& body) {
+        for (int w = 0; w < warm; ++w) body();
+        CK(cudaStreamSynchronize(st));
+        std::vector<float> ms(iters);
+        for (int i = 0; i < iters; ++i) {
+            CK(cudaEventRecord(e0, st)); body(); CK(cudaEventRecord(e1, st));
+            CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms[i], e0, e1));
+        }
+        std::sort(ms.begin(), ms.end());
+        return std::pair<float, float>(ms[iters / 2], ms[0]);
+    };
+    printf("name,ctas_per_sm,grid,median_ms,best_ms,median_gbs,best_gbs,ok\n");
+    if (!only) {
+        auto r = time_it([&] { CK(cudaMemcpyAsync(B.b, B.a, bytes, cudaMemcpyDeviceToDevice, st)); });
+        printf("memcpy_d2d,0,0,%.4f,%.4f,%.1f,%.1f,1\n", r.first, r.second, 2.0 * bytes / r.first / 1e6, 2.0 * bytes / r.second / 1e6);
+        for (int k : {4, 8, 16}) {
+            auto r2 = time_it([&] { plain_copy<<<sms * k, 512, 0, st>>>(B.a, B.b, B.n_vec); });
+            printf("plain_copy_t512,%d,%d,%.4f,%.4f,%.1f,%.1f,1\n", k, sms * k, r2.first, r2.second,
+                   2.0 * bytes / r2.first / 1e6, 2.0 * bytes / r2.second / 1e6);
+        }
+        // restore pattern in a (plain_copy/memcpy left b == a; a is intact)
+    }
+
+    unsigned long long seq = 0;
+    for (auto& c : cfgs) {
+        if (only && c.name.find(only) == std::string::npos) continue;
+        const int grid = sms * c.ctas_per_sm;
+        bool ok = true;
+        auto body = [&] {
+            const uint32_t next = B.seed * 1664525u + 1013904223u;
+            const uint4* s = B.cur == 0 ? B.a : B.b; uint4* d = B.cur == 0 ? B.b : B.a;
+            c.fn(s, d, B.n_vec, B.seed, B.seed ^ next, B.ctl, B.out_d, ++seq, grid, st);
+            B.seed = next; B.cur ^= 1;
+        };
+        // one checked launch first
+        const uint32_t seed_before = B.seed;
+        body();
+        cudaError_t le = cudaStreamSynchronize(st);
+        if (le != cudaSuccess) { printf("%s,%d,%d,0,0,0,0,CUDA_%s\n", c.name.c_str(), c.ctas_per_sm, grid, cudaGetErrorName(le)); return 3; }
+        const unsigned long long want = cpu_checksum(B.n_vec * 4, seed_before);
+        if (B.out_h->seq != seq || B.out_h->checksum != want || B.out_h->mismatches != 0) {
+            ok = false;
+            fprintf(stderr, "# %s k=%d: seq %llu/%llu checksum %llx want %llx mismatches %llu first_bad %llu\n", c.name.c_str(),
+                    c.ctas_per_sm, B.out_h->seq, seq, B.out_h->checksum, want, B.out_h->mismatches, B.out_h->first_bad);
+            // repair so later configs start clean
+            hbm_fill<256><<<sms * 8, 256, 0, st>>>(B.cur == 0 ? B.a : B.b, B.n_vec, B.seed);
+            CK(cudaStreamSynchronize(st));
+        }
+        auto r = time_it(body);
+        printf("%s,%d,%d,%.4f,%.4f,%.1f,%.1f,%d\n", c.name.c_str(), c.ctas_per_sm, grid, r.first, r.second,
+               2.0 * bytes / r.first / 1e6, 2.0 * bytes / r.second / 1e6, ok ? 1 : 0);
+        fflush(stdout);
+    }
+    return 0;
+}
