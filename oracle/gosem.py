@@ -58,6 +58,13 @@ def scanner_lines(data: bytes):
         yield line
 
 
+def scan(data: bytes):
+    """(lines, err): like draining a bufio.Scanner and then asking scanner.Err() != nil."""
+    lines = list(scanner_lines(data))
+    err = any(len(l) >= 64 * 1024 for l in data.split(b"\n"))
+    return lines, err
+
+
 def _lower(c):
     return c | 0x20 if 0x41 <= c <= 0x5A else c
 
