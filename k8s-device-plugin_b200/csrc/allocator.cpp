@@ -1,0 +1,384 @@
+// allocator.cpp -- best-effort topology allocator.
+//
+// Same answers as internal/pkg/allocator/{device.go,besteffort_policy.go}: pair weights
+// from kfd io_links/p2p_links files (or from a measured link list), grouping by physical
+// GPU, two-phase candidate enumeration, first-strictly-smallest selection.  Built
+// differently: link files are read once and parsed in a single pass, NodeIds are mapped to
+// a dense index and the pair weights live in a flat matrix so the candidate search does
+// no map lookups.
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "gosem.hpp"
+#include "internal.hpp"
+
+namespace b2dp {
+
+// device.go:38-54
+enum { kSameDevId = 10, kXgmiLink = 10, kSameNuma = 10, kDiffDevId = 20, kDiffNuma = 20, kPcieLink = 40, kOtherLink = 50 };
+
+int calculate_pair_weight(const Device& a, const Device& b, int link_type) {
+    int w = a.dev_id == b.dev_id ? kSameDevId : kDiffDevId;                       // device.go:137-141
+    w += link_type == 11 ? kXgmiLink : link_type == 2 ? kPcieLink : kOtherLink;   // device.go:143-149
+    w += a.numa == b.numa ? kSameNuma : kDiffNuma;                                // device.go:151-155
+    return w;
+}
+
+struct Partitions {  // device.go:75-80
+    std::string parent_id, dev_id;
+    std::vector<int> ids;
+};
+
+struct DeviceSet {  // device.go:67-73
+    std::vector<int> ids;
+    std::vector<int> parents;
+    int weight = 0;
+};
+
+class BestEffortPolicy {
+public:
+    std::vector<Device> devices;
+    std::unordered_map<std::string, int> by_id;    // devicesMap
+    std::map<std::string, Partitions> partitions;  // devicePartitions, keyed by DevId
+    std::map<int, std::map<int, int>> p2p;         // p2pWeights[from][to], from < to
+    std::unordered_map<int, int> node_index;       // dense view for the search
+    std::vector<int> dense;                        // n x n, [lo][hi] only
+    int n_nodes = 0;
+    std::mutex mu;
+
+    void build_dense() {
+        node_index.clear();
+        std::vector<int> nodes;
+        for (auto& d : devices) nodes.push_back(d.node_id);
+        for (auto& r : p2p) { nodes.push_back(r.first); for (auto& c : r.second) nodes.push_back(c.first); }
+        std::sort(nodes.begin(), nodes.end());
+        nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+        n_nodes = (int)nodes.size();
+        for (int i = 0; i < n_nodes; ++i) node_index[nodes[i]] = i;
+        dense.assign((size_t)n_nodes * n_nodes, 0);
+        for (auto& r : p2p)
+            for (auto& c : r.second) dense[(size_t)node_index[r.first] * n_nodes + node_index[c.first]] = c.second;
+    }
+    // p2pWeights[min(a,b)][max(a,b)], a missing entry reads as 0 (device.go:259-266)
+    int weight(int node_a, int node_b) const {
+        const int lo = std::min(node_a, node_b), hi = std::max(node_a, node_b);
+        auto ia = node_index.find(lo), ib = node_index.find(hi);
+        if (ia == node_index.end() || ib == node_index.end()) return 0;
+        return dense[(size_t)ia->second * n_nodes + ib->second];
+    }
+};
+
+BestEffortPolicy* policy_new() { return new BestEffortPolicy(); }
+void policy_free(BestEffortPolicy* p) { delete p; }
+
+// device.go:107-133, one pass: every line against every key, LAST match per key wins.
+// Returns false where the reference returns an error (open failure, ParseInt(…, 0, 32) error).
+static bool fetch_topo_properties(const std::string& path, const char* const* keys, int n_keys, int* res) {
+    std::string data;
+    for (int i = 0; i < n_keys; ++i) res[i] = 0;
+    if (!go::read_file(path, data)) return false;
+    bool ok = true;
+    go::scan_lines(data, [&](std::string_view line) {
+        for (int i = 0; i < n_keys; ++i) {
+            std::string_view digits;
+            if (!go::match_key_digits(line, keys[i], digits)) continue;
+            int64_t v;
+            if (go::parse_int(digits, 0, 32, &v) != go::NumErr::none) { ok = false; return false; }
+            res[i] = (int)v;
+        }
+        return true;
+    });
+    return ok;
+}
+
+// device.go:181-215 for one link record.
+static void apply_link(const std::vector<Device>& devs, const std::unordered_set<int>& lookup, int node_from,
+                       int node_to, int type, std::map<int, std::map<int, int>>& p2p) {
+    const int from = node_from < node_to ? node_from : node_to;
+    const int to = node_from < node_to ? node_to : node_from;
+    if (!lookup.count(from) || !lookup.count(to)) return;
+    const Device *fd = nullptr, *td = nullptr;
+    bool found = false;
+    for (const auto& d : devs) {  // device.go:198-209
+        if (d.node_id == from) fd = &d;
+        if (d.node_id == to) td = &d;
+        if (fd && td) { found = true; break; }
+    }
+    if (found) p2p[from][to] = calculate_pair_weight(*fd, *td, type);
+}
+
+static void finish_init(BestEffortPolicy* p, const std::vector<Device>& devs) {
+    // besteffort_policy.go:75-84 + device.go:287-304
+    p->devices = devs;
+    for (size_t i = 0; i < devs.size(); ++i) p->by_id[devs[i].id] = (int)i;
+    p->partitions.clear();
+    for (const auto& d : devs) {
+        auto& ps = p->partitions[d.dev_id];
+        ps.dev_id = d.dev_id;
+        if (d.id.find("amdgpu_xcp") == std::string::npos) ps.parent_id = d.id;  // device.go:297
+        ps.ids.push_back(d.node_id);
+    }
+    p->build_dense();
+}
+
+int policy_init_dir(BestEffortPolicy* p, const std::vector<Device>& devs, const std::string& dir_in) {
+    std::lock_guard<std::mutex> g(p->mu);
+    if (devs.empty()) return B2DP_E_ALLOC_EMPTY_DEVICES;  // device.go:221-225
+    const std::string dir = dir_in.empty() ? "/sys/class/kfd/kfd/topology/nodes" : dir_in;  // device.go:226-228
+    std::unordered_set<int> lookup;
+    for (auto& d : devs) lookup.insert(d.node_id);
+    static const char* const kMinor[] = {"drm_render_minor"};
+    static const char* const kLink[] = {"node_from", "node_to", "type"};
+    for (const auto& node_dir : go::glob_digit_prefixed(dir)) {
+        int minor;
+        if (!fetch_topo_properties(node_dir + "/properties", kMinor, 1, &minor) || minor <= 0) continue;  // device.go:240-244
+        std::vector<std::string> paths = go::glob_digit_prefixed(node_dir + "/io_links");
+        auto p2p_paths = go::glob_digit_prefixed(node_dir + "/p2p_links");
+        paths.insert(paths.end(), p2p_paths.begin(), p2p_paths.end());
+        for (const auto& lp : paths) {
+            int v[3];
+            if (!fetch_topo_properties(lp + "/properties", kLink, 3, v)) continue;  // device.go:176-179
+            apply_link(devs, lookup, v[0], v[1], v[2], p->p2p);
+        }
+    }
+    if (p->p2p.empty()) return B2DP_E_ALLOC_NO_WEIGHTS;  // besteffort_policy.go:72-74
+    finish_init(p, devs);
+    return B2DP_OK;
+}
+
+int policy_init_links(BestEffortPolicy* p, const std::vector<Device>& devs, const std::vector<Link>& links) {
+    std::lock_guard<std::mutex> g(p->mu);
+    if (devs.empty()) return B2DP_E_ALLOC_EMPTY_DEVICES;
+    std::unordered_set<int> lookup;
+    for (auto& d : devs) lookup.insert(d.node_id);
+    for (const auto& l : links) apply_link(devs, lookup, l.from, l.to, l.type, p->p2p);
+    if (p->p2p.empty()) return B2DP_E_ALLOC_NO_WEIGHTS;
+    finish_init(p, devs);
+    return B2DP_OK;
+}
+
+void policy_pair_weights(BestEffortPolicy* p, std::vector<b2dp_pair_weight>& out, int* n_rows) {
+    std::lock_guard<std::mutex> g(p->mu);
+    out.clear();
+    for (auto& r : p->p2p)
+        for (auto& c : r.second) out.push_back({r.first, c.first, c.second});
+    *n_rows = (int)p->p2p.size();
+}
+
+int policy_group_count(BestEffortPolicy* p) {
+    std::lock_guard<std::mutex> g(p->mu);
+    return (int)p->partitions.size();
+}
+
+// device.go:254-273
+static inline void add_device(const BestEffortPolicy* p, DeviceSet& s, int node) {
+    int w = s.weight;
+    for (int d : s.ids) w += p->weight(d, node);
+    s.weight = w;
+    s.ids.push_back(node);
+}
+
+// device.go:353-442.  `available`/`required` are device indices.  Returns error code or OK.
+static int candidate_subsets(const BestEffortPolicy* p, std::vector<int> available, const std::vector<int>& required,
+                             int size, std::vector<DeviceSet>& finals) {
+    finals.clear();
+    if (size <= 0) return B2DP_E_ALLOC_SUBSET_SIZE;
+    if ((int)available.size() < size) return B2DP_E_ALLOC_SUBSET_AVAIL;
+    const auto& devs = p->devices;
+    std::unordered_set<int> avail_nodes, req_nodes;
+    for (int i : available) avail_nodes.insert(devs[i].node_id);
+    for (int i : required) req_nodes.insert(devs[i].node_id);
+
+    // filterPartitions (device.go:310-351); ties on (len, ParentId) broken by DevId
+    std::vector<Partitions> groups;
+    for (const auto& kv : p->partitions) {
+        Partitions f;
+        for (int id : kv.second.ids)
+            if (!req_nodes.count(id) && avail_nodes.count(id)) f.ids.push_back(id);
+        if (f.ids.empty()) continue;
+        std::sort(f.ids.begin(), f.ids.end());
+        f.dev_id = kv.second.dev_id; f.parent_id = kv.second.parent_id;
+        groups.push_back(std::move(f));
+    }
+    std::stable_sort(groups.begin(), groups.end(), [](const Partitions& a, const Partitions& b) {
+        if (a.ids.size() != b.ids.size()) return a.ids.size() < b.ids.size();
+        if (a.parent_id != b.parent_id) return a.parent_id < b.parent_id;
+        return a.dev_id < b.dev_id;
+    });
+
+    const int new_size = size - (int)required.size();
+    const int n_groups = (int)groups.size();
+    auto add_required = [&](DeviceSet& s) { for (int r : required) add_device(p, s, devs[r].node_id); };
+
+    std::vector<DeviceSet> temp;
+    for (int idx = 0; idx < n_groups; ++idx) {  // phase 1, device.go:375-402
+        const auto& part = groups[idx];
+        DeviceSet s;
+        s.ids.push_back(part.ids[0]);
+        s.parents.push_back(idx);
+        if (new_size == 1) { add_required(s); finals.push_back(std::move(s)); continue; }
+        bool fulfilled = false;
+        for (int i = 1; i < (int)part.ids.size(); ++i) {
+            add_device(p, s, part.ids[i]);
+            if (i == new_size - 1) { fulfilled = true; break; }
+        }
+        if (fulfilled) { add_required(s); finals.push_back(std::move(s)); }
+        else temp.push_back(std::move(s));
+    }
+    for (size_t head = 0; head < temp.size(); ++head) {  // phase 2 (FIFO), device.go:405-440
+        // copy: temp may reallocate while we push
+        const DeviceSet cur = temp[head];
+        if ((int)cur.parents.size() == n_groups) continue;
+        for (int idx = 0; idx < n_groups; ++idx) {
+            if (std::find(cur.parents.begin(), cur.parents.end(), idx) != cur.parents.end()) continue;
+            DeviceSet s = cur;
+            s.parents.push_back(idx);
+            bool done = false;
+            for (int id : groups[idx].ids) {
+                add_device(p, s, id);
+                if ((int)s.ids.size() == new_size) {
+                    add_required(s);
+                    finals.push_back(s);
+                    done = true;
+                    break;
+                }
+            }
+            if (!done && (int)s.ids.size() < new_size) temp.push_back(std::move(s));
+        }
+    }
+    return B2DP_OK;
+}
+
+int policy_allocate(BestEffortPolicy* p, const std::vector<std::string>& avail, const std::vector<std::string>& req,
+                    int size, std::vector<std::string>& out, int* n_candidates, int* best_weight,
+                    bool candidates_only) {
+    std::lock_guard<std::mutex> g(p->mu);
+    out.clear();
+    if (n_candidates) *n_candidates = 0;
+    if (best_weight) *best_weight = 0;
+    auto to_indices = [&](const std::vector<std::string>& ids, std::vector<int>& idx) {
+        for (const auto& s : ids) {
+            auto it = p->by_id.find(s);
+            if (it == p->by_id.end()) return false;  // nil *Device => the reference panics
+            idx.push_back(it->second);
+        }
+        return true;
+    };
+    if (!candidates_only) {  // besteffort_policy.go:88-124
+        if (size <= 0) return B2DP_E_ALLOC_SIZE;
+        if ((int)avail.size() < size) return B2DP_E_ALLOC_AVAILABLE;
+        if ((int)req.size() > size) return B2DP_E_ALLOC_REQUIRED;
+        if (req.size() > avail.size()) return B2DP_E_ALLOC_REQ_AVAILABLE;
+        if (p->devices.empty()) return B2DP_E_ALLOC_INIT;
+        if ((int)avail.size() == size) { out = avail; return B2DP_OK; }
+        if ((int)req.size() == size) { out = req; return B2DP_OK; }
+        if (p->p2p.empty()) return B2DP_E_ALLOC_INIT;
+        for (const auto& r : req)  // setContainsAll, device.go:88-105
+            if (std::find(avail.begin(), avail.end(), r) == avail.end()) return B2DP_E_ALLOC_NOCANDIDATE;
+    }
+    std::vector<int> a_idx, r_idx;
+    if (!to_indices(avail, a_idx) || !to_indices(req, r_idx)) return B2DP_E_PANIC;
+    // device.go:362-364: available sorted by NodeId (stable here; Go's sort.Slice is not, which
+    // only matters for duplicate NodeIds)
+    std::stable_sort(a_idx.begin(), a_idx.end(),
+                     [&](int x, int y) { return p->devices[x].node_id < p->devices[y].node_id; });
+    std::vector<DeviceSet> finals;
+    int rc = candidate_subsets(p, a_idx, r_idx, size, finals);
+    if (rc != B2DP_OK) return rc;
+    int best = INT32_MAX;  // besteffort_policy.go:133-140
+    const DeviceSet* cand = nullptr;
+    for (const auto& s : finals)
+        if (s.weight < best) { cand = &s; best = s.weight; }
+    if (n_candidates) *n_candidates = (int)finals.size();
+    if (best_weight) *best_weight = cand ? cand->weight : 0;
+    if (candidates_only) return B2DP_OK;
+    if (!cand) return B2DP_E_PANIC;  // nil candidate deref, besteffort_policy.go:141
+    for (int id : cand->ids)         // besteffort_policy.go:141-148
+        for (int ai : a_idx)
+            if (p->devices[ai].node_id == id) { out.push_back(p->devices[ai].id); break; }
+    return B2DP_OK;
+}
+
+}  // namespace b2dp
+
+// ================================ C ABI ====================================================
+using namespace b2dp;
+
+struct b2dp_allocator { BestEffortPolicy* p; };
+
+extern "C" int b2dp_allocator_new(b2dp_allocator** out) {
+    if (!out) return B2DP_E_INVAL;
+    *out = new b2dp_allocator{policy_new()};
+    return B2DP_OK;
+}
+extern "C" void b2dp_allocator_free(b2dp_allocator* a) {
+    if (!a) return;
+    policy_free(a->p);
+    delete a;
+}
+static std::vector<Device> devs_from_abi(const b2dp_device* devs, int n) {
+    std::vector<Device> v;
+    for (int i = 0; i < n; ++i) v.push_back(from_abi(devs[i]));
+    return v;
+}
+extern "C" int b2dp_allocator_init(b2dp_allocator* a, const b2dp_device* devs, int n, const char* topo_nodes_dir) {
+    if (!a || n < 0 || (n && !devs)) return B2DP_E_INVAL;
+    return policy_init_dir(a->p, devs_from_abi(devs, n), topo_nodes_dir ? topo_nodes_dir : "");
+}
+extern "C" int b2dp_allocator_init_links(b2dp_allocator* a, const b2dp_device* devs, int n, const b2dp_link* links,
+                                         int n_links) {
+    if (!a || n < 0 || (n && !devs) || n_links < 0 || (n_links && !links)) return B2DP_E_INVAL;
+    std::vector<Link> l;
+    for (int i = 0; i < n_links; ++i) l.push_back({links[i].node_from, links[i].node_to, links[i].type});
+    return policy_init_links(a->p, devs_from_abi(devs, n), l);
+}
+extern "C" int b2dp_allocator_pair_weights(b2dp_allocator* a, b2dp_pair_weight* out, int cap, int* n, int* n_rows) {
+    if (!a || !n || cap < 0) return B2DP_E_INVAL;
+    std::vector<b2dp_pair_weight> v;
+    int rows = 0;
+    policy_pair_weights(a->p, v, &rows);
+    *n = (int)v.size();
+    if (n_rows) *n_rows = rows;
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    memcpy(out, v.data(), v.size() * sizeof(b2dp_pair_weight));
+    return B2DP_OK;
+}
+extern "C" int b2dp_allocator_group_count(b2dp_allocator* a, int32_t* groups) {
+    if (!a || !groups) return B2DP_E_INVAL;
+    *groups = policy_group_count(a->p);
+    return B2DP_OK;
+}
+static std::vector<std::string> strs(const char* const* p, int n) {
+    std::vector<std::string> v;
+    for (int i = 0; i < n; ++i) v.emplace_back(p[i] ? p[i] : "");
+    return v;
+}
+extern "C" int b2dp_allocator_candidates(b2dp_allocator* a, const char* const* available, int na,
+                                         const char* const* required, int nr, int size, int32_t* n_candidates,
+                                         int32_t* best_weight) {
+    if (!a || na < 0 || nr < 0 || (na && !available) || (nr && !required)) return B2DP_E_INVAL;
+    std::vector<std::string> out;
+    int nc = 0, bw = 0;
+    int rc = policy_allocate(a->p, strs(available, na), strs(required, nr), size, out, &nc, &bw, true);
+    if (n_candidates) *n_candidates = nc;
+    if (best_weight) *best_weight = bw;
+    return rc;
+}
+extern "C" int b2dp_allocator_allocate(b2dp_allocator* a, const char* const* available, int na,
+                                       const char* const* required, int nr, int size, char (*out)[64], int cap,
+                                       int* n) {
+    if (!a || !n || na < 0 || nr < 0 || (na && !available) || (nr && !required) || cap < 0) return B2DP_E_INVAL;
+    std::vector<std::string> ids;
+    *n = 0;
+    int rc = policy_allocate(a->p, strs(available, na), strs(required, nr), size, ids, nullptr, nullptr, false);
+    if (rc != B2DP_OK) return rc;
+    *n = (int)ids.size();
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    for (int i = 0; i < *n; ++i) copy_str(out[i], 64, ids[i]);
+    return B2DP_OK;
+}

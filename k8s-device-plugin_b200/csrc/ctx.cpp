@@ -1,0 +1,624 @@
+// ctx.cpp -- context object, backend dispatch and the context-level C ABI
+// (enumerate / health / ListAndWatch / Allocate / GetPreferredAllocation / labels / export).
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <chrono>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "gosem.hpp"
+#include "internal.hpp"
+#include "pbwire.hpp"
+
+using namespace b2dp;
+
+namespace {
+const char kHealthy[] = "Healthy";      // v1beta1/constants.go:21
+const char kUnhealthy[] = "Unhealthy";  // v1beta1/constants.go:23
+thread_local std::string t_last_error;
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+struct b2dp_ctx {
+    enum Kind { KFD, CUDA } kind = KFD;
+    std::string sysroot;        // kfd: plays "/"; cuda: where numa_node is looked up
+    CudaBackend* cuda = nullptr;
+    std::mutex mu;              // guards policy / allocator_init_error / links
+    BestEffortPolicy* policy = nullptr;
+    bool started = false, allocator_init_error = false;
+    std::vector<Link> links;    // cuda: measured link list (node ids), filled by the p2p matrix
+    bool have_links = false;
+    std::vector<float> p2p_gbs; // last matrix, n x n
+};
+
+static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
+
+static int enumerate_ctx(b2dp_ctx* c, std::vector<Device>& devs) {
+    std::string err;
+    int rc = c->kind == b2dp_ctx::KFD ? kfd_enumerate(c->sysroot, devs, err) : cuda_enumerate(c->cuda, devs, err);
+    if (rc != B2DP_OK) t_last_error = err;
+    return rc;
+}
+
+extern "C" const char* b2dp_strerror(int code) {
+    switch (code) {
+        case B2DP_OK: return "ok";
+        case B2DP_E_INVAL: return "invalid argument";
+        case B2DP_E_NOSPC: return "output capacity too small";
+        case B2DP_E_IO: return "i/o error";
+        case B2DP_E_NOTFOUND: return "Topology property not found.";
+        case B2DP_E_SYNTAX: return "invalid syntax";
+        case B2DP_E_RANGE: return "value out of range";
+        case B2DP_E_NODRIVER: return "amdgpu driver unavailable. exiting with exit code 2.";
+        case B2DP_E_NOGPU: return "no usable CUDA device";
+        case B2DP_E_CUDA: return "CUDA error";
+        case B2DP_E_TIMEOUT: return "probe deadline expired";
+        case B2DP_E_UNSUPPORTED: return "not supported by this backend";
+        case B2DP_E_PANIC: return "the reference would panic on this input";
+        case B2DP_E_NOMEM: return "out of memory";
+        case B2DP_E_HETEROGENEOUS:
+            return "Partitions of different styles across GPUs in a node is not supported with single strategy. "
+                   "Please start device plugin with mixed strategy";
+        case B2DP_E_ALLOC_SIZE: return "allocation size can not be negative";
+        case B2DP_E_ALLOC_AVAILABLE: return "available devices count less than allocation size";
+        case B2DP_E_ALLOC_REQUIRED: return "must_include devices size is more than allocation size";
+        case B2DP_E_ALLOC_REQ_AVAILABLE: return "must_include length should be less than or equal to avilable device size";
+        case B2DP_E_ALLOC_INIT: return "Init method must be called before Allocate";
+        case B2DP_E_ALLOC_NOCANDIDATE: return "No candidate subset found with matching criteria";
+        case B2DP_E_ALLOC_EMPTY_DEVICES: return "Devices list is empty. Unable to calculate pair wise weights";
+        case B2DP_E_ALLOC_NO_WEIGHTS: return "Besteffort Policy init failed to initialize p2pWeights";
+        case B2DP_E_ALLOC_SUBSET_SIZE: return "subset size should be positive integer";
+        case B2DP_E_ALLOC_SUBSET_AVAIL: return "subset size is more than available devices";
+    }
+    return "unknown error";
+}
+extern "C" int b2dp_abi_version(void) { return B2DP_ABI_VERSION; }
+
+// ---- open / close ------------------------------------------------------------------------
+static bool parse_kv(const std::string& body, std::map<std::string, std::string>& kv) {
+    size_t pos = 0;
+    while (pos < body.size()) {
+        size_t e = body.find(',', pos);
+        if (e == std::string::npos) e = body.size();
+        std::string item = body.substr(pos, e - pos);
+        pos = e + 1;
+        if (item.empty()) continue;
+        size_t eq = item.find('=');
+        if (eq == std::string::npos) return false;
+        kv[item.substr(0, eq)] = item.substr(eq + 1);
+    }
+    return true;
+}
+
+extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
+    if (!uri || !out) return B2DP_E_INVAL;
+    *out = nullptr;
+    const std::string u = uri;
+    if (u.compare(0, 4, "kfd:") == 0) {
+        auto* c = new b2dp_ctx();
+        c->kind = b2dp_ctx::KFD;
+        c->sysroot = u.substr(4);
+        if (c->sysroot.empty()) c->sysroot = "/";
+        if (!go::exists(go::join(c->sysroot, "sys/module/amdgpu/drivers/"))) {  // amdgpu.go:150-152
+            delete c;
+            return fail(B2DP_E_NODRIVER, "amdgpu driver unavailable under " + u.substr(4));
+        }
+        *out = c;
+        return B2DP_OK;
+    }
+    if (u.compare(0, 5, "cuda:") == 0) {
+        std::map<std::string, std::string> kv;
+        if (!parse_kv(u.substr(5), kv)) return fail(B2DP_E_INVAL, "bad cuda: uri");
+        CudaConfig cfg;
+        for (auto& p : kv) {
+            if (p.first == "devices") {
+                size_t pos = 0;
+                while (pos <= p.second.size()) {
+                    size_t e = p.second.find('+', pos);
+                    if (e == std::string::npos) e = p.second.size();
+                    if (e > pos) cfg.devices.push_back(atoi(p.second.substr(pos, e - pos).c_str()));
+                    pos = e + 1;
+                }
+            } else if (p.first == "bytes") cfg.bytes = strtoull(p.second.c_str(), nullptr, 0);
+            else if (p.first == "p2p_bytes") cfg.p2p_bytes = strtoull(p.second.c_str(), nullptr, 0);
+            else if (p.first == "min_gbs") cfg.min_gbs = (float)atof(p.second.c_str());
+            else if (p.first == "sysroot") cfg.sysroot = p.second;
+            else return fail(B2DP_E_INVAL, "unknown cuda: option " + p.first);
+        }
+        if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");
+        std::string err;
+        CudaBackend* be = nullptr;
+        int rc = cuda_backend_open(cfg, &be, err);
+        if (rc != B2DP_OK) return fail(rc, err);
+        auto* c = new b2dp_ctx();
+        c->kind = b2dp_ctx::CUDA;
+        c->sysroot = cfg.sysroot;
+        c->cuda = be;
+        *out = c;
+        return B2DP_OK;
+    }
+    return fail(B2DP_E_INVAL, "unknown backend uri (want kfd:<sysroot> or cuda:[opts])");
+}
+
+extern "C" void b2dp_close(b2dp_ctx* c) {
+    if (!c) return;
+    if (c->cuda) cuda_backend_close(c->cuda);
+    if (c->policy) policy_free(c->policy);
+    delete c;
+}
+
+extern "C" const char* b2dp_last_error(b2dp_ctx*) { return t_last_error.c_str(); }
+
+// ---- enumerate & friends -----------------------------------------------------------------
+extern "C" int b2dp_enumerate(b2dp_ctx* c, b2dp_device* out, int cap, int* n) {
+    if (!c || !n || cap < 0) return B2DP_E_INVAL;
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    *n = (int)devs.size();
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    for (int i = 0; i < *n; ++i) to_abi(devs[i], &out[i]);
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_partition_histogram(b2dp_ctx* c, b2dp_kv_count* out, int cap, int* n) {
+    if (!c || !n || cap < 0) return B2DP_E_INVAL;
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    auto h = partition_histogram(devs);
+    *n = (int)h.size();
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    int i = 0;
+    for (auto& kv : h) { memset(&out[i], 0, sizeof out[i]); copy_str(out[i].key, 64, kv.first); out[i].count = kv.second; ++i; }
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_is_homogeneous(b2dp_ctx* c, int32_t* homogeneous) {
+    if (!c || !homogeneous) return B2DP_E_INVAL;
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    *homogeneous = partition_histogram(devs).size() <= 1 ? 1 : 0;
+    return B2DP_OK;
+}
+
+static void label_source(b2dp_ctx* c, LabelSource& src) {
+    src.sysroot = c->sysroot;
+    if (c->kind == b2dp_ctx::CUDA) cuda_label_source(c->cuda, src);
+}
+
+extern "C" int b2dp_partition_supported(b2dp_ctx* c, int which, int32_t* supported) {
+    if (!c || !supported || which < 0 || which > 1) return B2DP_E_INVAL;
+    if (c->kind == b2dp_ctx::KFD) *supported = kfd_partition_supported(c->sysroot, which) ? 1 : 0;
+    else { LabelSource s; label_source(c, s); *supported = s.part_supported[which] ? 1 : 0; }
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_resource_list(b2dp_ctx* c, const char* strategy, char (*names)[64], int cap, int* n) {
+    if (!c || !n || cap < 0) return B2DP_E_INVAL;
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    std::vector<std::string> res;
+    rc = resource_list(devs, strategy, res);
+    if (rc != B2DP_OK) return rc;
+    *n = (int)res.size();
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !names) return B2DP_E_INVAL;
+    for (int i = 0; i < *n; ++i) copy_str(names[i], 64, res[i]);
+    return B2DP_OK;
+}
+
+static bool node_health(b2dp_ctx* c) {
+    if (c->kind == b2dp_ctx::KFD) return kfd_simple_health_check(go::join(c->sysroot, "sys/class/kfd/kfd"));
+    return cuda_node_health(c->cuda) == 1;
+}
+
+extern "C" int b2dp_node_health(b2dp_ctx* c, int32_t* healthy) {
+    if (!c || !healthy) return B2DP_E_INVAL;
+    *healthy = node_health(c) ? 1 : 0;
+    return B2DP_OK;
+}
+
+// ---- probe -------------------------------------------------------------------------------
+extern "C" int b2dp_probe_health(b2dp_ctx* c, const b2dp_probe_opts* opts, b2dp_probe_result* out, int cap, int* n) {
+    if (!c || !n || cap < 0) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA)
+        return fail(B2DP_E_UNSUPPORTED, "the GPU health probe needs the cuda: backend (there is no CPU fallback)");
+    std::vector<b2dp_probe_result> res;
+    std::string err;
+    int rc = cuda_probe(c->cuda, opts, res, err);
+    if (rc != B2DP_OK) return fail(rc, err);
+    *n = (int)res.size();
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    memcpy(out, res.data(), res.size() * sizeof(b2dp_probe_result));
+    return B2DP_OK;
+}
+extern "C" int b2dp_probe_inject_fault(b2dp_ctx* c, int device, uint64_t word_index, uint32_t mask) {
+    if (!c) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "cuda: backend only");
+    std::string err;
+    int rc = cuda_inject_fault(c->cuda, device, word_index, mask, err);
+    return rc == B2DP_OK ? rc : fail(rc, err);
+}
+extern "C" int b2dp_probe_reset(b2dp_ctx* c, int device) {
+    if (!c) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "cuda: backend only");
+    std::string err;
+    int rc = cuda_probe_reset(c->cuda, device, err);
+    return rc == B2DP_OK ? rc : fail(rc, err);
+}
+extern "C" int b2dp_probe_peek(b2dp_ctx* c, int device, uint64_t word_index, uint32_t* out, uint64_t n_words) {
+    if (!c || (!out && n_words)) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "cuda: backend only");
+    std::string err;
+    int rc = cuda_probe_peek(c->cuda, device, word_index, out, n_words, err);
+    return rc == B2DP_OK ? rc : fail(rc, err);
+}
+
+extern "C" int b2dp_merge_health(const char (*ids)[64], int n, int32_t default_healthy, int have_source,
+                                 const char (*src_ids)[64], const int32_t* src_health, int m, int32_t* out) {
+    if (n < 0 || m < 0 || (n && (!ids || !out)) || (have_source && m && (!src_ids || !src_health))) return B2DP_E_INVAL;
+    // health.go:86-106; hMap built at health.go:74-80 (later entries overwrite earlier ones)
+    std::map<std::string, int> hmap;
+    if (have_source)
+        for (int j = 0; j < m; ++j) hmap[src_ids[j]] = src_health[j] ? 1 : 0;
+    for (int i = 0; i < n; ++i) {
+        if (!have_source) { out[i] = default_healthy ? 1 : 0; continue; }
+        auto it = hmap.find(ids[i]);
+        out[i] = it != hmap.end() ? it->second : (default_healthy ? 1 : 0);
+    }
+    return B2DP_OK;
+}
+
+// ---- ListAndWatch ------------------------------------------------------------------------
+extern "C" int b2dp_list_and_watch(b2dp_ctx* c, const char* resource, const b2dp_cycle_opts* opts, uint8_t* buf,
+                                   size_t cap, size_t* len, b2dp_cycle_stats* stats) {
+    if (!c || !len) return B2DP_E_INVAL;
+    const double t0 = now_ms();
+    b2dp_cycle_stats st{};
+    const uint32_t flags = opts ? opts->flags : B2DP_LW_INITIAL;
+    const bool heartbeat = (flags & B2DP_LW_HEARTBEAT) != 0;
+    *len = 0;
+
+    // plugin.go:231-237: GetAMDGPUs + IsHomogeneous (the reference enumerates twice; one
+    // enumeration serves both here)
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    const bool homogeneous = partition_histogram(devs).size() <= 1;
+    st.homogeneous = homogeneous;
+    const double t1 = now_ms();
+    st.ms_enumerate = (float)(t1 - t0);
+
+    // plugin.go:241-299: which devices this resource's stream carries
+    std::vector<const Device*> sel;
+    if (homogeneous) for (auto& d : devs) sel.push_back(&d);
+    else {
+        const std::string want = resource ? resource : "";
+        for (auto& d : devs) if (d.compute + "_" + d.memory == want) sel.push_back(&d);
+        if (sel.empty()) { st.ms_total = (float)(now_ms() - t0); if (stats) *stats = st; return B2DP_OK; }
+    }
+
+    std::vector<int> healthy(sel.size(), 1);
+    st.node_healthy = 1;
+    if (heartbeat) {
+        const bool def = node_health(c);  // plugin.go:305-309
+        st.node_healthy = def;
+        std::map<std::string, int> hmap;
+        bool have_source = false;
+        if (flags & B2DP_LW_EXTERNAL_SOURCE) {
+            have_source = true;
+            for (int j = 0; opts && j < opts->src_n; ++j) hmap[opts->src_ids[j]] = opts->src_health[j] ? 1 : 0;
+        } else if (!(flags & B2DP_LW_NO_PROBE) && c->kind == b2dp_ctx::CUDA) {
+            std::vector<b2dp_probe_result> res;
+            std::string err;
+            const double p0 = now_ms();
+            rc = cuda_probe(c->cuda, opts ? &opts->probe : nullptr, res, err);
+            st.ms_probe = (float)(now_ms() - p0);
+            if (rc != B2DP_OK) return fail(rc, err);
+            // the probe answers per enumerated device (same order as devs)
+            have_source = true;
+            st.probe_gbs_min = 1e30f;
+            for (auto& r : res) {
+                if (r.device >= 0 && r.device < (int)devs.size()) hmap[devs[r.device].id] = r.healthy;
+                st.probe_bytes += r.bytes;
+                st.probe_gbs_sum += r.gbs;
+                if (r.gbs < st.probe_gbs_min) st.probe_gbs_min = r.gbs;
+            }
+            if (res.empty()) st.probe_gbs_min = 0;
+        }
+        for (size_t i = 0; i < sel.size(); ++i) {  // health.go:93-105
+            if (!have_source) { healthy[i] = def; continue; }
+            auto it = hmap.find(sel[i]->id);
+            healthy[i] = it != hmap.end() ? it->second : (int)def;
+        }
+    }
+
+    const double e0 = now_ms();
+    std::string wire;
+    wire.reserve(sel.size() * 48);
+    for (size_t i = 0; i < sel.size(); ++i) {
+        pb::encode_device(wire, sel[i]->id, healthy[i] ? kHealthy : kUnhealthy, sel[i]->numa);
+        if (!healthy[i]) st.n_unhealthy++;
+    }
+    st.n_devices = (int)sel.size();
+    st.ms_encode = (float)(now_ms() - e0);
+    *len = wire.size();
+    st.ms_total = (float)(now_ms() - t0);
+    if (stats) *stats = st;
+    if (wire.size() > cap) return B2DP_E_NOSPC;
+    if (!wire.empty() && !buf) return B2DP_E_INVAL;
+    memcpy(buf, wire.data(), wire.size());
+    return B2DP_OK;
+}
+
+// ---- Allocate ----------------------------------------------------------------------------
+static int device_specs(b2dp_ctx* c, const char* const* ids, int n_ids, std::vector<b2dp_devspec>& specs) {
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    auto push = [&](const std::string& p) {
+        b2dp_devspec s{};
+        copy_str(s.host_path, sizeof s.host_path, p);
+        copy_str(s.container_path, sizeof s.container_path, p);
+        copy_str(s.permissions, sizeof s.permissions, "rw");
+        specs.push_back(s);
+    };
+    if (c->kind == b2dp_ctx::KFD) push("/dev/kfd");  // plugin.go:364-370
+    else { push("/dev/nvidiactl"); push("/dev/nvidia-uvm"); push("/dev/nvidia-uvm-tools"); }
+    for (int i = 0; i < n_ids; ++i) {
+        const std::string id = ids[i] ? ids[i] : "";
+        for (const auto& d : devs) {
+            if (d.id != id) continue;
+            if (c->kind == b2dp_ctx::KFD) {  // plugin.go:375-386 (canonical order: card, renderD)
+                push("/dev/dri/card" + std::to_string(d.card));
+                push("/dev/dri/renderD" + std::to_string(d.render_d));
+            } else push("/dev/nvidia" + std::to_string(d.card));
+            break;
+        }
+    }
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_device_specs(b2dp_ctx* c, const char* const* ids, int n_ids, b2dp_devspec* out, int cap, int* n) {
+    if (!c || !n || n_ids < 0 || (n_ids && !ids) || cap < 0) return B2DP_E_INVAL;
+    std::vector<b2dp_devspec> specs;
+    int rc = device_specs(c, ids, n_ids, specs);
+    if (rc != B2DP_OK) return rc;
+    *n = (int)specs.size();
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    memcpy(out, specs.data(), specs.size() * sizeof(b2dp_devspec));
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_allocate_response(b2dp_ctx* c, const char* const* ids, int n_ids, uint8_t* buf, size_t cap,
+                                      size_t* len) {
+    if (!c || !len || n_ids < 0 || (n_ids && !ids)) return B2DP_E_INVAL;
+    std::vector<b2dp_devspec> specs;
+    int rc = device_specs(c, ids, n_ids, specs);
+    if (rc != B2DP_OK) return rc;
+    std::string wire;
+    for (auto& s : specs) pb::encode_devspec(wire, 3, s.container_path, s.host_path, s.permissions);
+    *len = wire.size();
+    if (wire.size() > cap) return B2DP_E_NOSPC;
+    if (!wire.empty() && !buf) return B2DP_E_INVAL;
+    memcpy(buf, wire.data(), wire.size());
+    return B2DP_OK;
+}
+
+// ---- Start / GetPreferredAllocation ------------------------------------------------------
+static int ensure_links(b2dp_ctx* c, const std::vector<Device>& devs) {
+    if (c->have_links) return B2DP_OK;
+    const int n = (int)devs.size();
+    std::vector<float> gbs((size_t)n * n);
+    std::vector<int32_t> type((size_t)n * n);
+    std::vector<uint64_t> mism((size_t)n * n);
+    std::string err;
+    int rc = cuda_p2p_matrix(c->cuda, nullptr, gbs.data(), type.data(), mism.data(), n, err);
+    if (rc != B2DP_OK) return fail(rc, err);
+    c->links.clear();
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+            if (i != j) c->links.push_back({devs[i].node_id, devs[j].node_id, type[(size_t)i * n + j]});
+    c->p2p_gbs = gbs;
+    c->have_links = true;
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_start(b2dp_ctx* c) {
+    if (!c) return B2DP_E_INVAL;
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);  // plugin.go:85 getDevices()
+    if (rc != B2DP_OK) return rc;
+    std::lock_guard<std::mutex> g(c->mu);
+    if (c->policy) { policy_free(c->policy); c->policy = nullptr; }
+    c->policy = policy_new();
+    if (c->kind == b2dp_ctx::KFD) rc = policy_init_dir(c->policy, devs, go::join(c->sysroot, "sys/class/kfd/kfd/topology/nodes"));
+    else {
+        rc = ensure_links(c, devs);
+        if (rc == B2DP_OK) rc = policy_init_links(c->policy, devs, c->links);
+    }
+    c->started = true;
+    c->allocator_init_error = rc != B2DP_OK;  // plugin.go:86-90
+    if (rc != B2DP_OK && t_last_error.empty()) t_last_error = b2dp_strerror(rc);
+    return rc;
+}
+
+extern "C" int b2dp_preferred_allocation_available(b2dp_ctx* c, int32_t* available) {
+    if (!c || !available) return B2DP_E_INVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    *available = c->allocator_init_error ? 0 : 1;  // plugin.go:210-217
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_preferred_allocation(b2dp_ctx* c, const char* const* available, int na,
+                                         const char* const* must_include, int nm, int size, char (*out)[64], int cap,
+                                         int* n) {
+    if (!c || !n || na < 0 || nm < 0 || (na && !available) || (nm && !must_include) || cap < 0) return B2DP_E_INVAL;
+    BestEffortPolicy* p;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (!c->policy) c->policy = policy_new();  // Allocate before Start => "Init method must be called"
+        p = c->policy;
+    }
+    std::vector<std::string> a, r, ids;
+    for (int i = 0; i < na; ++i) a.emplace_back(available[i] ? available[i] : "");
+    for (int i = 0; i < nm; ++i) r.emplace_back(must_include[i] ? must_include[i] : "");
+    *n = 0;
+    int rc = policy_allocate(p, a, r, size, ids, nullptr, nullptr, false);
+    if (rc != B2DP_OK) return fail(rc, std::string("unable to get preferred allocation list. Error:") + b2dp_strerror(rc));
+    *n = (int)ids.size();
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    for (int i = 0; i < *n; ++i) copy_str(out[i], 64, ids[i]);
+    return B2DP_OK;
+}
+
+// ---- p2p ---------------------------------------------------------------------------------
+extern "C" int b2dp_p2p_matrix(b2dp_ctx* c, const b2dp_p2p_opts* opts, float* gbs, int32_t* link_type,
+                               uint64_t* mismatches, int n) {
+    if (!c || !gbs || !link_type || n <= 0) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "the P2P matrix needs the cuda: backend");
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    if ((int)devs.size() != n) return fail(B2DP_E_INVAL, "n must equal the device count");
+    std::vector<uint64_t> mism((size_t)n * n);
+    std::string err;
+    rc = cuda_p2p_matrix(c->cuda, opts, gbs, link_type, mism.data(), n, err);
+    if (rc != B2DP_OK) return fail(rc, err);
+    if (mismatches) memcpy(mismatches, mism.data(), mism.size() * sizeof(uint64_t));
+    std::lock_guard<std::mutex> g(c->mu);
+    c->links.clear();
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+            if (i != j) c->links.push_back({devs[i].node_id, devs[j].node_id, link_type[(size_t)i * n + j]});
+    c->p2p_gbs.assign(gbs, gbs + (size_t)n * n);
+    c->have_links = true;
+    return B2DP_OK;
+}
+
+// ---- labels ------------------------------------------------------------------------------
+int b2dp_emit_labels_internal(const std::map<std::string, std::string>& m, b2dp_label* out, int cap, int* n);
+
+extern "C" int b2dp_generate_labels(b2dp_ctx* c, const char* enabled, b2dp_label* out, int cap, int* n) {
+    if (!c || !enabled || !n || cap < 0) return B2DP_E_INVAL;
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);  // main.go:385
+    if (rc != B2DP_OK) return rc;
+    LabelSource src;
+    label_source(c, src);
+    std::map<std::string, std::string> m;
+    rc = generate_labels(devs, src, enabled, m);
+    if (rc != B2DP_OK) return rc;
+    return b2dp_emit_labels_internal(m, out, cap, n);
+}
+
+// ---- kfd-tree export ---------------------------------------------------------------------
+static bool mkdirs(const std::string& p) {
+    std::string cur;
+    size_t pos = 0;
+    while (pos <= p.size()) {
+        size_t e = p.find('/', pos);
+        if (e == std::string::npos) e = p.size();
+        cur = p.substr(0, e);
+        pos = e + 1;
+        if (cur.empty()) continue;
+        if (::mkdir(cur.c_str(), 0755) != 0 && errno != EEXIST) return false;
+    }
+    return true;
+}
+static bool write_file(const std::string& path, const std::string& data) {
+    if (!mkdirs(go::dir(path))) return false;
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+    fclose(f);
+    return ok;
+}
+
+extern "C" int b2dp_export_kfd_tree(b2dp_ctx* c, const char* dir_c) {
+    if (!c || !dir_c || !*dir_c) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "export is for the cuda: backend (kfd trees already are one)");
+    std::vector<Device> devs;
+    int rc = enumerate_ctx(c, devs);
+    if (rc != B2DP_OK) return rc;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        rc = ensure_links(c, devs);
+        if (rc != B2DP_OK) return rc;
+    }
+    LabelSource src;
+    label_source(c, src);
+    const std::string dir = dir_c;
+    const std::string nodes = dir + "/sys/class/kfd/kfd/topology/nodes";
+    int min_node = INT32_MAX;
+    for (auto& d : devs) min_node = std::min(min_node, d.node_id);
+    if (devs.empty()) min_node = 1;
+    bool ok = true;
+    // CPU nodes 0 .. min_node-1
+    for (int k = 0; k < min_node; ++k)
+        ok &= write_file(nodes + "/" + std::to_string(k) + "/properties",
+                         "cpu_cores_count 64\nsimd_count 0\nmem_banks_count 1\ncaches_count 0\nio_links_count 0\n"
+                         "cpu_core_id_base 0\nsimd_id_base 0\nvendor_id 0\ndevice_id 0\nlocation_id 0\ndomain 0\n"
+                         "drm_render_minor 0\n");
+    for (size_t i = 0; i < devs.size(); ++i) {
+        const Device& d = devs[i];
+        unsigned dom = 0, bus = 0, dv = 0;
+        sscanf(d.dev_id.c_str(), "%x:%x:%x", &dom, &bus, &dv);
+        const long long loc = ((long long)bus << 8) | ((long long)dv << 3);
+        const long long sms = i < src.sm_count.size() ? src.sm_count[i] : 0;
+        const long long vram = i < src.vram_bytes.size() ? src.vram_bytes[i] : 0;
+        std::string devid_hex = i < src.device_id.size() ? src.device_id[i] : "0x0";
+        char props[1024];
+        snprintf(props, sizeof props,
+                 "cpu_cores_count 0\nsimd_count %lld\nmem_banks_count 1\ncaches_count 0\nio_links_count %zu\n"
+                 "cpu_core_id_base 0\nsimd_id_base 0\nmax_waves_per_simd 16\nwave_front_size 32\nsimd_per_cu 4\n"
+                 "gfx_target_version 100000\nvendor_id 4318\ndevice_id %ld\nlocation_id %lld\ndomain %u\n"
+                 "drm_render_minor %d\nlocal_mem_size %lld\n",
+                 sms * 4, devs.size() - 1, strtol(devid_hex.c_str(), nullptr, 16), loc, dom, d.render_d, vram);
+        const std::string nd = nodes + "/" + std::to_string(d.node_id);
+        ok &= write_file(nd + "/properties", props);
+        char mb[256];
+        snprintf(mb, sizeof mb, "heap_type 1\nsize_in_bytes %lld\nflags 0\nwidth 8192\nmem_clk_max 3996\n", vram);
+        ok &= write_file(nd + "/mem_banks/0/properties", mb);
+        int li = 0;
+        for (const auto& l : c->links) {
+            if (l.from != d.node_id) continue;
+            char lp[512];
+            snprintf(lp, sizeof lp,
+                     "type %d\nversion_major 0\nversion_minor 0\nnode_from %d\nnode_to %d\nweight %d\nmin_latency 0\n"
+                     "max_latency 0\nmin_bandwidth 0\nmax_bandwidth 0\nrecommended_transfer_size 0\nflags 1\n",
+                     l.type, l.from, l.to, l.type == 11 ? 15 : 20);
+            ok &= write_file(nd + "/io_links/" + std::to_string(li++) + "/properties", lp);
+        }
+        // driver dir (amdgpu.go:155-217) + drm class files the label generators read
+        const std::string pci = dir + "/sys/module/amdgpu/drivers/pci:amdgpu/" + d.id;
+        ok &= write_file(pci + "/numa_node", std::to_string(d.numa) + "\n");
+        ok &= mkdirs(pci + "/drm/card" + std::to_string(d.card));
+        ok &= mkdirs(pci + "/drm/renderD" + std::to_string(d.render_d));
+        if (src.part_supported[0]) ok &= write_file(pci + "/available_compute_partition", "SPX\n");
+        if (src.part_supported[1]) ok &= write_file(pci + "/available_memory_partition", "NPS1\n");
+        const std::string drm = dir + "/sys/class/drm/card" + std::to_string(d.card) + "/device";
+        ok &= write_file(drm + "/device", devid_hex + "\n");
+        ok &= write_file(drm + "/product_name", (i < src.product_name.size() ? src.product_name[i] : "") + "\n");
+        ok &= write_file(drm + "/driver/module/version", src.driver_version + "\n");
+        ok &= write_file(drm + "/driver/module/srcversion", src.driver_src_version + "\n");
+    }
+    ok &= mkdirs(dir + "/sys/devices/platform");
+    return ok ? B2DP_OK : fail(B2DP_E_IO, "failed writing the kfd tree under " + dir);
+}

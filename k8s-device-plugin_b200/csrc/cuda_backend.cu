@@ -1,0 +1,630 @@
+// cuda_backend.cu -- the `cuda:` backend: real B200s.
+//
+// One worker thread per GPU owns that GPU's primary context, stream, events, pinned result
+// block and the two probe buffers; callers (cgo threads, ctypes, gRPC handlers) never touch
+// a CUDA "current device".  A probe request is posted to every worker before any is waited
+// on, so the N kernels run concurrently; a worker that does not answer before the deadline
+// yields B2DP_E_TIMEOUT / Unhealthy for its device only.
+//
+// Replaces: the node-level text check `simpleHealthCheck` (plugin.go:161-206), the exporter
+// round trip `getGPUHealth` (exporter/health.go:42-82) and the kfd link `type` read
+// (allocator/device.go:143-149).  Enumeration replaces GetAMDGPUs (amdgpu.go:149-268) with
+// CUDA/NVML/sysfs queries; the record layout and id formats are the reference's.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <functional>
+#include <thread>
+
+#include "gosem.hpp"
+#include "hbm_probe.cuh"
+#include "internal.hpp"
+
+namespace b2dp {
+
+// ---- kernel shapes chosen from profiles/r01_sweep1_kernel_variants.csv --------------------
+constexpr int kTmaCW = 4;           // verifier warps
+constexpr int kTmaTileVec = 1024;   // 16 KiB tiles
+constexpr int kTmaStages = 3;
+constexpr int kTmaCtasPerSm = 2;    // 2 x 3 x 16 KiB = 96 KiB staged per SM
+constexpr size_t kTmaSmem = (size_t)kTmaStages * kTmaTileVec * 16 + 2 * kTmaStages * 8;
+constexpr int kRegThreads = 512, kRegUnroll = 2, kRegCtasPerSm = 2;
+constexpr int kP2pThreads = 512, kP2pUnroll = 4, kP2pCtasPerSm = 4;
+
+// bit b of (uint32(i) * K) summed over i < n_words, for the closed-form checksum
+__global__ void pattern_bit_counts(unsigned long long n_words, unsigned long long* counts /*[32]*/) {
+    unsigned int c[32];  // per-thread iterations stay far below 2^32 for any buffer that fits in HBM
+#pragma unroll
+    for (int b = 0; b < 32; ++b) c[b] = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        const uint32_t m = (uint32_t)i * kPatternMul;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) c[b] += (m >> b) & 1u;
+    }
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+        unsigned long long v = c[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[b], v);
+    }
+}
+
+// ---- NVML (optional, resolved at run time) ---------------------------------------------------
+struct Nvml {
+    void* lib = nullptr;
+    int (*init)() = nullptr;
+    int (*driver_version)(char*, unsigned) = nullptr;
+    int (*handle_by_bus_id)(const char*, void**) = nullptr;
+    int (*minor_number)(void*, unsigned*) = nullptr;
+    int (*vbios)(void*, char*, unsigned) = nullptr;
+    int (*mig_mode)(void*, unsigned*, unsigned*) = nullptr;
+    bool ok = false;
+    void load() {
+        lib = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) return;
+        init = (int (*)())dlsym(lib, "nvmlInit_v2");
+        driver_version = (int (*)(char*, unsigned))dlsym(lib, "nvmlSystemGetDriverVersion");
+        handle_by_bus_id = (int (*)(const char*, void**))dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2");
+        minor_number = (int (*)(void*, unsigned*))dlsym(lib, "nvmlDeviceGetMinorNumber");
+        vbios = (int (*)(void*, char*, unsigned))dlsym(lib, "nvmlDeviceGetVbiosVersion");
+        mig_mode = (int (*)(void*, unsigned*, unsigned*))dlsym(lib, "nvmlDeviceGetMigMode");
+        ok = init && init() == 0;
+    }
+};
+
+struct Completion {
+    std::mutex mu;
+    std::condition_variable cv;
+    bool done = false;
+    void signal() { { std::lock_guard<std::mutex> g(mu); done = true; } cv.notify_all(); }
+    bool wait_until(std::chrono::steady_clock::time_point tp) {
+        std::unique_lock<std::mutex> l(mu);
+        return cv.wait_until(l, tp, [&] { return done; });
+    }
+    void wait() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return done; }); }
+};
+
+struct Gpu {
+    int ordinal = 0;
+    Device dev;                 // the enumerate record
+    std::string name, pci_device_id, vbios, family;
+    int64_t vram = 0, sms = 0;
+    bool mig_capable = false;
+    // worker
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool quit = false;
+    // state owned by the worker thread
+    uint4* buf[2] = {nullptr, nullptr};
+    ProbeCtl* ctl = nullptr;
+    ProbeOut *out_h = nullptr, *out_d = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    uint32_t seed = 0;
+    int cur = 0;
+    unsigned long long seq = 0;
+    std::vector<char> peer_enabled;
+};
+
+class CudaBackend {
+public:
+    CudaConfig cfg;
+    std::vector<std::unique_ptr<Gpu>> gpus;  // sorted by dev.id
+    Nvml nvml;
+    std::string driver_version, driver_src_version;
+    std::mutex probe_mu;  // one fan-out at a time
+    std::mutex bc_mu;
+    std::map<unsigned long long, std::array<unsigned long long, 32>> bitcounts;
+    unsigned long long n_vec() const { return cfg.bytes / 16; }
+};
+
+static std::string cuda_err(const char* what, cudaError_t e) {
+    return std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+}
+
+static void worker_loop(Gpu* g) {
+    cudaSetDevice(g->ordinal);
+    for (;;) {
+        std::function<void()> fn;
+        {
+            std::unique_lock<std::mutex> l(g->mu);
+            g->cv.wait(l, [&] { return g->quit || !g->q.empty(); });
+            if (g->q.empty()) return;  // quit
+            fn = std::move(g->q.front());
+            g->q.pop_front();
+        }
+        fn();
+    }
+}
+
+// Run fn on g's worker; returns the completion to wait on.
+static std::shared_ptr<Completion> post(Gpu* g, std::function<void()> fn) {
+    auto c = std::make_shared<Completion>();
+    {
+        std::lock_guard<std::mutex> l(g->mu);
+        g->q.push_back([fn = std::move(fn), c] { fn(); c->signal(); });
+    }
+    g->cv.notify_one();
+    return c;
+}
+template <class F>
+static void run_sync(Gpu* g, F&& fn) { post(g, std::forward<F>(fn))->wait(); }
+
+// closed-form checksum of a clean buffer of n_words with `seed`
+static unsigned long long expected_checksum(const std::array<unsigned long long, 32>& c, unsigned long long n_words,
+                                            uint32_t seed) {
+    unsigned long long s = 0;
+    for (int b = 0; b < 32; ++b) {
+        const unsigned long long ones = ((seed >> b) & 1u) ? n_words - c[b] : c[b];
+        s += ones << b;
+    }
+    return s;
+}
+
+static int get_bitcounts(CudaBackend* be, unsigned long long n_words, std::array<unsigned long long, 32>& out,
+                         std::string& err) {
+    std::lock_guard<std::mutex> l(be->bc_mu);
+    auto it = be->bitcounts.find(n_words);
+    if (it != be->bitcounts.end()) { out = it->second; return B2DP_OK; }
+    Gpu* g = be->gpus[0].get();
+    cudaError_t ce = cudaSuccess;
+    std::array<unsigned long long, 32> host{};
+    run_sync(g, [&] {
+        unsigned long long* d = nullptr;
+        if ((ce = cudaMalloc(&d, 32 * sizeof(unsigned long long))) != cudaSuccess) return;
+        cudaMemsetAsync(d, 0, 32 * sizeof(unsigned long long), g->stream);
+        pattern_bit_counts<<<(int)g->sms * 4, 256, 0, g->stream>>>(n_words, d);
+        ce = cudaMemcpyAsync(host.data(), d, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(g->stream);
+        cudaFree(d);
+    });
+    if (ce != cudaSuccess) { err = cuda_err("pattern_bit_counts", ce); return B2DP_E_CUDA; }
+    be->bitcounts[n_words] = host;
+    out = host;
+    return B2DP_OK;
+}
+
+static std::string read_trim(const std::string& p) {
+    std::string d;
+    if (!go::read_file(p, d)) return "";
+    return go::trim_space(d);
+}
+
+int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err) {
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        err = ce != cudaSuccess ? cuda_err("cudaGetDeviceCount", ce) : "no CUDA devices";
+        return B2DP_E_NOGPU;
+    }
+    auto be = std::make_unique<CudaBackend>();
+    be->cfg = cfg;
+    be->nvml.load();
+    std::vector<int> ords = cfg.devices;
+    if (ords.empty()) for (int i = 0; i < count; ++i) ords.push_back(i);
+    for (int o : ords) if (o < 0 || o >= count) { err = "device ordinal out of range"; return B2DP_E_INVAL; }
+
+    if (be->nvml.ok && be->nvml.driver_version) {
+        char buf[96] = {0};
+        if (be->nvml.driver_version(buf, sizeof buf) == 0) be->driver_version = buf;
+    }
+    if (be->driver_version.empty()) be->driver_version = read_trim("/sys/module/nvidia/version");
+    be->driver_src_version = read_trim("/sys/module/nvidia/srcversion");
+
+    // CPU topology nodes precede GPU nodes in a kfd tree; count NUMA nodes (>= 1)
+    int n_cpu = 0;
+    for (auto& p : go::glob_prefixed(go::join(cfg.sysroot, "sys/devices/system/node"), "node"))
+        if (p.size() > 4 && go::is_digit(p.back())) ++n_cpu;
+    if (n_cpu < 1) n_cpu = 1;
+
+    for (int o : ords) {
+        auto g = std::make_unique<Gpu>();
+        g->ordinal = o;
+        cudaDeviceProp prop;
+        if ((ce = cudaGetDeviceProperties(&prop, o)) != cudaSuccess) { err = cuda_err("cudaGetDeviceProperties", ce); return B2DP_E_CUDA; }
+        char bdf[32];
+        snprintf(bdf, sizeof bdf, "%04x:%02x:%02x.0", prop.pciDomainID, prop.pciBusID, prop.pciDeviceID);
+        g->dev.id = bdf;  // same shape as the reference's PCI dir names (amdgpu.go:154-155)
+        char devid[32];
+        snprintf(devid, sizeof devid, "%04x:%02x:%02x:0", prop.pciDomainID, prop.pciBusID, prop.pciDeviceID);  // amdgpu.go:141
+        g->dev.dev_id = devid;
+        g->name = prop.name;
+        g->vram = (int64_t)prop.totalGlobalMem;
+        g->sms = prop.multiProcessorCount;
+        g->family = prop.major == 10 || prop.major == 12 ? "Blackwell" : prop.major == 9 ? "Hopper"
+                    : prop.major == 8 ? (prop.minor == 9 ? "Ada" : "Ampere") : "sm_" + std::to_string(prop.major * 10 + prop.minor);
+        const std::string pci_dir = go::join(cfg.sysroot, std::string("sys/bus/pci/devices/") + bdf);
+        g->pci_device_id = read_trim(pci_dir + "/device");
+        if (g->pci_device_id.empty()) g->pci_device_id = "0x0000";
+        std::string numa = read_trim(pci_dir + "/numa_node");
+        int64_t nv = 0;
+        g->dev.numa = (!numa.empty() && go::atoi(numa, &nv) == go::NumErr::none) ? (int)nv : 0;
+        // /dev/nvidia<minor>
+        g->dev.card = o;
+        bool have_minor = false;
+        if (be->nvml.ok && be->nvml.handle_by_bus_id && be->nvml.minor_number) {
+            void* h = nullptr;
+            char busid[32];
+            snprintf(busid, sizeof busid, "%08x:%02x:%02x.0", prop.pciDomainID, prop.pciBusID, prop.pciDeviceID);
+            if (be->nvml.handle_by_bus_id(busid, &h) == 0) {
+                unsigned mn = 0;
+                if (be->nvml.minor_number(h, &mn) == 0) { g->dev.card = (int)mn; have_minor = true; }
+                char vb[64] = {0};
+                if (be->nvml.vbios && be->nvml.vbios(h, vb, sizeof vb) == 0) g->vbios = vb;
+                unsigned cur = 0, pend = 0;
+                if (be->nvml.mig_mode && be->nvml.mig_mode(h, &cur, &pend) == 0) g->mig_capable = true;
+            }
+        }
+        if (!have_minor) {
+            std::string info;
+            if (go::read_file(std::string("/proc/driver/nvidia/gpus/") + bdf + "/information", info)) {
+                size_t p = info.find("Device Minor:");
+                if (p != std::string::npos) g->dev.card = atoi(info.c_str() + p + 13);
+            }
+        }
+        be->gpus.push_back(std::move(g));
+    }
+    std::sort(be->gpus.begin(), be->gpus.end(), [](const auto& a, const auto& b) { return a->dev.id < b->dev.id; });
+    for (size_t i = 0; i < be->gpus.size(); ++i) {
+        be->gpus[i]->dev.render_d = 128 + (int)i;
+        be->gpus[i]->dev.node_id = n_cpu + (int)i;
+        be->gpus[i]->peer_enabled.assign(be->gpus.size(), 0);
+    }
+
+    // start workers and allocate per-GPU state on them
+    for (auto& gp : be->gpus) gp->th = std::thread(worker_loop, gp.get());
+    std::vector<std::shared_ptr<Completion>> cs;
+    std::vector<cudaError_t> errs(be->gpus.size(), cudaSuccess);
+    std::vector<const char*> where(be->gpus.size(), "");
+    for (size_t i = 0; i < be->gpus.size(); ++i) {
+        Gpu* g = be->gpus[i].get();
+        const unsigned long long bytes = cfg.bytes, n_vec = cfg.bytes / 16;
+        const int idx = (int)i;
+        cs.push_back(post(g, [g, bytes, n_vec, idx, &errs, &where] {
+            cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) { errs[idx] = e; where[idx] = #x; return; }
+            TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+            TRY(cudaEventCreate(&g->e0));
+            TRY(cudaEventCreate(&g->e1));
+            TRY(cudaMalloc(&g->buf[0], bytes));
+            TRY(cudaMalloc(&g->buf[1], bytes));
+            TRY(cudaMalloc(&g->ctl, sizeof(ProbeCtl)));
+            ProbeCtl init{};
+            init.first_bad = ~0ull; init.t_start_ns = ~0ull;
+            TRY(cudaMemcpy(g->ctl, &init, sizeof init, cudaMemcpyHostToDevice));
+            TRY(cudaHostAlloc(&g->out_h, sizeof(ProbeOut), cudaHostAllocMapped));
+            memset(g->out_h, 0, sizeof(ProbeOut));
+            TRY(cudaHostGetDevicePointer(&g->out_d, g->out_h, 0));
+            TRY(cudaFuncSetAttribute(hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
+            TRY(cudaFuncSetAttribute(hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            g->seed = 0x5EED0000u | (uint32_t)(idx & 0xffff);
+            g->cur = 0;
+            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[0], n_vec, g->seed);
+            TRY(cudaGetLastError());
+            TRY(cudaStreamSynchronize(g->stream));
+#undef TRY
+        }));
+    }
+    for (auto& c : cs) c->wait();
+    for (size_t i = 0; i < errs.size(); ++i)
+        if (errs[i] != cudaSuccess) {
+            err = cuda_err(where[i], errs[i]) + " on " + be->gpus[i]->dev.id;
+            CudaBackend* raw = be.release();
+            cuda_backend_close(raw);
+            return B2DP_E_CUDA;
+        }
+    *out = be.release();
+    return B2DP_OK;
+}
+
+void cuda_backend_close(CudaBackend* be) {
+    if (!be) return;
+    for (auto& gp : be->gpus) {
+        Gpu* g = gp.get();
+        if (!g->th.joinable()) continue;
+        post(g, [g] {
+            if (g->stream) cudaStreamSynchronize(g->stream);
+            if (g->buf[0]) cudaFree(g->buf[0]);
+            if (g->buf[1]) cudaFree(g->buf[1]);
+            if (g->ctl) cudaFree(g->ctl);
+            if (g->out_h) cudaFreeHost(g->out_h);
+            if (g->e0) cudaEventDestroy(g->e0);
+            if (g->e1) cudaEventDestroy(g->e1);
+            if (g->stream) cudaStreamDestroy(g->stream);
+        })->wait();
+        { std::lock_guard<std::mutex> l(g->mu); g->quit = true; }
+        g->cv.notify_all();
+        g->th.join();
+    }
+    delete be;
+}
+
+int cuda_device_count(CudaBackend* be) { return (int)be->gpus.size(); }
+float cuda_min_gbs(CudaBackend* be) { return be->cfg.min_gbs; }
+
+int cuda_enumerate(CudaBackend* be, std::vector<Device>& out, std::string&) {
+    out.clear();
+    for (auto& g : be->gpus) out.push_back(g->dev);
+    return B2DP_OK;
+}
+
+int cuda_node_health(CudaBackend* be) {
+    // the analogue of "a GPU node exists in the kfd topology" (plugin.go:198-201):
+    // the driver still answers and reports the devices this context was opened on
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count >= (int)be->gpus.size() && !be->gpus.empty() ? 1 : 0;
+}
+
+void cuda_label_source(CudaBackend* be, LabelSource& src) {
+    src.native = true;
+    src.driver_version = be->driver_version;
+    src.driver_src_version = be->driver_src_version;
+    bool mig = !be->gpus.empty();
+    for (auto& g : be->gpus) {
+        src.family.push_back(g->family);
+        src.product_name.push_back(g->name);
+        src.device_id.push_back(g->pci_device_id);
+        src.vbios.push_back(g->vbios);
+        src.vram_bytes.push_back(g->vram);
+        src.sm_count.push_back(g->sms);
+        mig = mig && g->mig_capable;
+    }
+    src.part_supported[0] = src.part_supported[1] = mig;
+}
+
+// ---- the probe fan-out -----------------------------------------------------------------------
+struct ProbeJobResult {
+    cudaError_t ce = cudaSuccess;
+    ProbeOut out{};
+    float ms = 0;
+    uint32_t seed = 0;
+    bool seq_ok = false;
+};
+
+static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uint32_t seed, uint32_t delta,
+                         const uint4* src, uint4* dst, unsigned long long seq) {
+    if (variant == B2DP_PROBE_VARIANT_R128)
+        hbm_probe_r128<kRegThreads, kRegUnroll><<<(int)g->sms * kRegCtasPerSm, kRegThreads, 0, g->stream>>>(
+            src, dst, n_vec, seed, delta, g->ctl, g->out_d, seq);
+    else
+        hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>
+            <<<(int)g->sms * kTmaCtasPerSm, (kTmaCW + 1) * 32, kTmaSmem, g->stream>>>(src, dst, n_vec, seed, delta,
+                                                                                    g->ctl, g->out_d, seq);
+}
+
+int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_probe_result>& out, std::string& err) {
+    std::lock_guard<std::mutex> pl(be->probe_mu);
+    const unsigned long long n_vec = be->n_vec(), n_words = n_vec * 4;
+    std::array<unsigned long long, 32> bc;
+    int rc = get_bitcounts(be, n_words, bc, err);
+    if (rc != B2DP_OK) return rc;
+    const uint32_t variant = opts ? (opts->flags & B2DP_PROBE_VARIANT_MASK) : 0;
+    const uint32_t timeout_ms = opts && opts->timeout_ms ? opts->timeout_ms : 5000;  // health.go:37
+    const float min_gbs = opts && opts->min_gbs > 0 ? opts->min_gbs : be->cfg.min_gbs;
+    const size_t n = be->gpus.size();
+    std::vector<std::shared_ptr<ProbeJobResult>> res(n);
+    std::vector<std::shared_ptr<Completion>> cs(n);
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
+    for (size_t i = 0; i < n; ++i) {  // launch everywhere before waiting anywhere
+        Gpu* g = be->gpus[i].get();
+        auto r = std::make_shared<ProbeJobResult>();
+        res[i] = r;
+        cs[i] = post(g, [g, r, n_vec, variant] {
+            const uint32_t seed = g->seed, next = seed * 1664525u + 1013904223u;
+            const unsigned long long seq = ++g->seq;
+            r->seed = seed;
+            cudaEventRecord(g->e0, g->stream);
+            launch_probe(g, n_vec, variant, seed, seed ^ next, g->buf[g->cur], g->buf[g->cur ^ 1], seq);
+            cudaError_t e = cudaGetLastError();
+            cudaEventRecord(g->e1, g->stream);
+            if (e == cudaSuccess) e = cudaEventSynchronize(g->e1);
+            if (e == cudaSuccess) e = cudaEventElapsedTime(&r->ms, g->e0, g->e1);
+            r->ce = e;
+            if (e != cudaSuccess) return;
+            memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // published before the event fired
+            r->seq_ok = r->out.seq == seq;
+            g->seed = next;
+            g->cur ^= 1;
+            if (r->out.mismatches != 0 || !r->seq_ok) {
+                // report once, then start the next pass from a clean pattern: a transient flip is
+                // reported exactly once, a stuck cell shows up again on the next pass
+                hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
+                cudaStreamSynchronize(g->stream);
+            }
+        });
+    }
+    out.assign(n, b2dp_probe_result{});
+    for (size_t i = 0; i < n; ++i) {
+        b2dp_probe_result& o = out[i];
+        o.device = (int)i;
+        o.bytes = 2ull * be->cfg.bytes;
+        o.first_bad_word = ~0ull;
+        if (!cs[i]->wait_until(deadline)) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; continue; }
+        const ProbeJobResult& r = *res[i];
+        o.seed = r.seed;
+        o.expected_checksum = expected_checksum(bc, n_words, r.seed);
+        if (r.ce != cudaSuccess) {
+            o.err = B2DP_E_CUDA; o.healthy = 0;
+            err = cuda_err("probe", r.ce) + " on " + be->gpus[i]->dev.id;
+            continue;
+        }
+        o.checksum = r.out.checksum;
+        o.mismatches = r.out.mismatches;
+        o.first_bad_word = r.out.first_bad;
+        o.ms_event = r.ms;
+        o.ms_device = (float)((double)(r.out.t_end_ns - r.out.t_start_ns) * 1e-6);
+        o.gbs = r.ms > 0 ? (float)((double)o.bytes / (double)r.ms * 1e-6) : 0.f;
+        // verdict (oracle/probe.py probe_healthy)
+        o.healthy = (r.seq_ok && o.mismatches == 0 && o.checksum == o.expected_checksum && o.gbs >= min_gbs) ? 1 : 0;
+    }
+    return B2DP_OK;
+}
+
+static Gpu* gpu_at(CudaBackend* be, int device, std::string& err) {
+    if (device < 0 || device >= (int)be->gpus.size()) { err = "device index out of range"; return nullptr; }
+    return be->gpus[device].get();
+}
+
+int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask, std::string& err) {
+    Gpu* g = gpu_at(be, device, err);
+    if (!g) return B2DP_E_INVAL;
+    if (word >= be->n_vec() * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
+    cudaError_t ce = cudaSuccess;
+    run_sync(g, [&] {
+        hbm_poke<<<1, 1, 0, g->stream>>>(reinterpret_cast<uint32_t*>(g->buf[g->cur]), word, mask);
+        ce = cudaStreamSynchronize(g->stream);
+    });
+    if (ce != cudaSuccess) { err = cuda_err("hbm_poke", ce); return B2DP_E_CUDA; }
+    return B2DP_OK;
+}
+
+int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
+    const unsigned long long n_vec = be->n_vec();
+    for (int i = 0; i < (int)be->gpus.size(); ++i) {
+        if (device >= 0 && device != i) continue;
+        Gpu* g = be->gpus[i].get();
+        cudaError_t ce = cudaSuccess;
+        run_sync(g, [&] {
+            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
+            ce = cudaStreamSynchronize(g->stream);
+        });
+        if (ce != cudaSuccess) { err = cuda_err("hbm_fill", ce); return B2DP_E_CUDA; }
+    }
+    if (device >= (int)be->gpus.size()) { err = "device index out of range"; return B2DP_E_INVAL; }
+    return B2DP_OK;
+}
+
+int cuda_probe_peek(CudaBackend* be, int device, uint64_t word, uint32_t* out, uint64_t n, std::string& err) {
+    Gpu* g = gpu_at(be, device, err);
+    if (!g) return B2DP_E_INVAL;
+    if (word + n > be->n_vec() * 4) { err = "range out of bounds"; return B2DP_E_INVAL; }
+    cudaError_t ce = cudaSuccess;
+    run_sync(g, [&] {
+        ce = cudaMemcpyAsync(out, reinterpret_cast<const uint32_t*>(g->buf[g->cur]) + word, n * 4, cudaMemcpyDeviceToHost,
+                             g->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(g->stream);
+    });
+    if (ce != cudaSuccess) { err = cuda_err("peek", ce); return B2DP_E_CUDA; }
+    return B2DP_OK;
+}
+
+// ---- P2P matrix ------------------------------------------------------------------------------
+constexpr float kNvlinkRefGbs = 770.f, kNvlinkClassFraction = 0.25f;  // oracle/probe.py
+
+int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int32_t* link_type, uint64_t* mism, int n,
+                    std::string& err) {
+    std::lock_guard<std::mutex> pl(be->probe_mu);
+    if (n != (int)be->gpus.size()) { err = "n must equal the device count"; return B2DP_E_INVAL; }
+    unsigned long long bytes = opts && opts->bytes ? opts->bytes : be->cfg.p2p_bytes;
+    if (bytes > be->cfg.bytes) bytes = be->cfg.bytes;
+    bytes &= ~15ull;
+    const unsigned long long n_vec = bytes / 16;
+    const int iters = opts && opts->iters ? (int)opts->iters : 2;
+    for (int i = 0; i < n * n; ++i) { gbs[i] = 0; link_type[i] = 0; mism[i] = 0; }
+    std::array<unsigned long long, 32> bc;
+    int rc = get_bitcounts(be, n_vec * 4, bc, err);
+    if (rc != B2DP_OK) return rc;
+
+    // peer capability + enable (on the reader's worker)
+    std::vector<char> can((size_t)n * n, 0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            int c = 0;
+            cudaDeviceCanAccessPeer(&c, be->gpus[i]->ordinal, be->gpus[j]->ordinal);
+            can[(size_t)i * n + j] = (char)c;
+            if (c && !be->gpus[i]->peer_enabled[j]) {
+                Gpu* g = be->gpus[i].get();
+                const int peer = be->gpus[j]->ordinal;
+                cudaError_t ce = cudaSuccess;
+                run_sync(g, [&] {
+                    ce = cudaDeviceEnablePeerAccess(peer, 0);
+                    if (ce == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ce = cudaSuccess; }
+                });
+                if (ce != cudaSuccess) can[(size_t)i * n + j] = 0;
+                else g->peer_enabled[j] = 1;
+            }
+        }
+
+    struct PairRes { cudaError_t ce = cudaSuccess; float best_ms = 1e30f; ProbeOut out{}; bool ran = false; };
+    auto run_pair = [&](int i, int j, PairRes* pr) {
+        // GPU i reads GPU j's current pattern buffer into its own spare buffer
+        Gpu* g = be->gpus[i].get();
+        Gpu* peer = be->gpus[j].get();
+        const uint4* src = peer->buf[peer->cur];
+        const uint32_t seed = peer->seed;
+        return post(g, [g, src, seed, n_vec, iters, pr] {
+            pr->ran = true;
+            for (int it = 0; it < iters + 1; ++it) {  // first iteration is a warm-up
+                const unsigned long long seq = ++g->seq;
+                cudaEventRecord(g->e0, g->stream);
+                hbm_probe_r128<kP2pThreads, kP2pUnroll><<<(int)g->sms * kP2pCtasPerSm, kP2pThreads, 0, g->stream>>>(
+                    src, g->buf[g->cur ^ 1], n_vec, seed, 0u, g->ctl, g->out_d, seq);
+                cudaError_t e = cudaGetLastError();
+                cudaEventRecord(g->e1, g->stream);
+                if (e == cudaSuccess) e = cudaEventSynchronize(g->e1);
+                float ms = 0;
+                if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, g->e0, g->e1);
+                if (e != cudaSuccess) { pr->ce = e; return; }
+                memcpy(&pr->out, (const void*)g->out_h, sizeof(ProbeOut));
+                if (it > 0 && ms < pr->best_ms) pr->best_ms = ms;
+            }
+        });
+    };
+
+    // N-1 rounds of disjoint matchings (circle method); both directions of a pair run together
+    const int m = n % 2 ? n + 1 : n;
+    for (int r = 0; r < m - 1 && n > 1; ++r) {
+        std::vector<std::pair<int, int>> pairs;
+        auto add = [&](int a, int b) { if (a < n && b < n) pairs.push_back({a, b}); };  // >= n: bye
+        add(m - 1, r);
+        for (int k = 1; k < m / 2; ++k) add((r + k) % (m - 1), (r - k + (m - 1)) % (m - 1));
+        std::vector<std::unique_ptr<PairRes>> prs;
+        std::vector<std::shared_ptr<Completion>> cs;
+        std::vector<std::pair<int, int>> dirs;
+        for (auto& p : pairs)
+            for (int d = 0; d < 2; ++d) {
+                const int i = d ? p.second : p.first, j = d ? p.first : p.second;
+                if (!can[(size_t)i * n + j]) continue;
+                prs.push_back(std::make_unique<PairRes>());
+                dirs.push_back({i, j});
+                cs.push_back(run_pair(i, j, prs.back().get()));
+            }
+        for (auto& c : cs) c->wait();
+        for (size_t k = 0; k < dirs.size(); ++k) {
+            const int i = dirs[k].first, j = dirs[k].second;
+            const PairRes& pr = *prs[k];
+            if (pr.ce != cudaSuccess) { err = cuda_err("p2p_probe", pr.ce); return B2DP_E_CUDA; }
+            const float g_ = (float)((double)bytes / (double)pr.best_ms * 1e-6);
+            gbs[(size_t)i * n + j] = g_;
+            uint64_t bad = pr.out.mismatches;
+            if (pr.out.checksum != expected_checksum(bc, n_vec * 4, be->gpus[j]->seed)) bad = bad ? bad : 1;
+            mism[(size_t)i * n + j] = bad;
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            // oracle/probe.py classify_link
+            link_type[(size_t)i * n + j] = !can[(size_t)i * n + j] ? 0
+                : gbs[(size_t)i * n + j] >= kNvlinkClassFraction * kNvlinkRefGbs ? 11 : 2;
+        }
+    return B2DP_OK;
+}
+
+}  // namespace b2dp

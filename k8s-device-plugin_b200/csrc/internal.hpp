@@ -1,0 +1,111 @@
+// internal.hpp -- shared internal declarations of libb200dp (not part of the ABI).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200dp.h"
+
+namespace b2dp {
+
+struct Device {
+    std::string id, dev_id, compute, memory;
+    int card = 0, render_d = 128, node_id = 0, numa = -1;
+};
+
+inline void copy_str(char* dst, size_t cap, const std::string& s) {
+    size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(dst, s.data(), n);
+    dst[n] = 0;
+}
+inline void to_abi(const Device& d, b2dp_device* o) {
+    memset(o, 0, sizeof *o);
+    copy_str(o->id, sizeof o->id, d.id);
+    copy_str(o->dev_id, sizeof o->dev_id, d.dev_id);
+    copy_str(o->compute_partition, sizeof o->compute_partition, d.compute);
+    copy_str(o->memory_partition, sizeof o->memory_partition, d.memory);
+    o->card = d.card; o->render_d = d.render_d; o->node_id = d.node_id; o->numa_node = d.numa;
+}
+inline Device from_abi(const b2dp_device& a) {
+    Device d;
+    d.id = a.id; d.dev_id = a.dev_id; d.compute = a.compute_partition; d.memory = a.memory_partition;
+    d.card = a.card; d.render_d = a.render_d; d.node_id = a.node_id; d.numa = a.numa_node;
+    return d;
+}
+
+// ---- kfd.cpp: sysfs/kfd readers -------------------------------------------------------
+struct TopoMaps {
+    std::map<int, std::string> dev_ids;  // render minor -> devID   (amdgpu.go:101-146)
+    std::map<int, int> node_ids;         // render minor -> node id (amdgpu.go:496-538)
+};
+void kfd_topology_maps(const std::string& topo_root, TopoMaps& out);
+// GetAMDGPUs on <sysroot>; returns B2DP_OK / B2DP_E_NODRIVER / B2DP_E_PANIC. Sorted by id.
+int kfd_enumerate(const std::string& sysroot, std::vector<Device>& out, std::string& err);
+int kfd_parse_property(const std::string& path, const char* key, int64_t* value);
+bool kfd_simple_health_check(const std::string& topo_root);
+int kfd_count_gpu_dev(const std::string& topo_root);
+bool kfd_partition_supported(const std::string& sysroot, int which);
+std::map<std::string, int> partition_histogram(const std::vector<Device>& devs);
+// main.go:53-91; returns B2DP_OK or B2DP_E_HETEROGENEOUS / B2DP_E_INVAL.
+int resource_list(const std::vector<Device>& devs, const char* strategy, std::vector<std::string>& out);
+
+// ---- allocator.cpp --------------------------------------------------------------------
+struct Link { int from, to, type; };
+class BestEffortPolicy;
+BestEffortPolicy* policy_new();
+void policy_free(BestEffortPolicy*);
+int policy_init_dir(BestEffortPolicy*, const std::vector<Device>&, const std::string& topo_nodes_dir);
+int policy_init_links(BestEffortPolicy*, const std::vector<Device>&, const std::vector<Link>&);
+int policy_allocate(BestEffortPolicy*, const std::vector<std::string>& avail, const std::vector<std::string>& req,
+                    int size, std::vector<std::string>& out, int* n_candidates, int* best_weight,
+                    bool candidates_only);
+void policy_pair_weights(BestEffortPolicy*, std::vector<b2dp_pair_weight>& out, int* n_rows);
+int policy_group_count(BestEffortPolicy*);
+// Pair weights as kfd link files would give them, for the kfd-tree export.
+int calculate_pair_weight(const Device& a, const Device& b, int link_type);
+
+// ---- labels.cpp -----------------------------------------------------------------------
+struct LabelSource {  // what the generators read; filled by the backend
+    std::string sysroot;  // for kfd-style reads
+    // cuda backend answers (one entry per enumerated device, same order)
+    bool native = false;
+    std::vector<std::string> family, product_name, device_id, vbios;
+    std::vector<int64_t> vram_bytes, sm_count;
+    std::string driver_version, driver_src_version;
+    bool part_supported[2] = {false, false};
+};
+void create_labels(const std::string& kind, const std::map<std::string, int>& entries,
+                   std::map<std::string, std::string>& out);
+extern const char* const kGeneratorNames[12];
+int generate_labels(const std::vector<Device>& devs, const LabelSource& src, const std::string& enabled_csv,
+                    std::map<std::string, std::string>& out);
+void remove_old_node_labels(std::map<std::string, std::string>& labels);
+
+// ---- cuda_backend.cu -------------------------------------------------------------------
+class CudaBackend;
+struct CudaConfig {
+    std::vector<int> devices;  // empty = all
+    uint64_t bytes = 1ull << 30;
+    uint64_t p2p_bytes = 256ull << 20;
+    float min_gbs = 3000.f;
+    std::string sysroot = "/";
+};
+int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err);
+void cuda_backend_close(CudaBackend*);
+int cuda_enumerate(CudaBackend*, std::vector<Device>& out, std::string& err);
+int cuda_node_health(CudaBackend*);
+int cuda_probe(CudaBackend*, const b2dp_probe_opts* opts, std::vector<b2dp_probe_result>& out, std::string& err);
+int cuda_inject_fault(CudaBackend*, int device, uint64_t word, uint32_t mask, std::string& err);
+int cuda_probe_reset(CudaBackend*, int device, std::string& err);
+int cuda_probe_peek(CudaBackend*, int device, uint64_t word, uint32_t* out, uint64_t n, std::string& err);
+int cuda_p2p_matrix(CudaBackend*, const b2dp_p2p_opts* opts, float* gbs, int32_t* link_type, uint64_t* mism, int n,
+                    std::string& err);
+int cuda_device_count(CudaBackend*);
+void cuda_label_source(CudaBackend*, LabelSource& src);
+float cuda_min_gbs(CudaBackend*);
+
+}  // namespace b2dp
