@@ -1,0 +1,181 @@
+"""GPU parity tests (run with -m gpu on a B200): every result comes through the C ABI
+(libb200dp.so, cuda: backend) and is compared bit-exactly with the oracle (oracle/probe.py for
+the probe arithmetic; the reference-restating oracle on the exported kfd tree for enumerate /
+pair weights / allocation / labels).  Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import allocator as oalloc
+from oracle import amdgpu as oamd
+from oracle import labeller as olab
+from oracle import plugin as oplug
+from oracle import probe as oprobe
+
+pytestmark = pytest.mark.gpu
+
+MiB = 1 << 20
+
+
+@pytest.fixture(scope="module")
+def P(pkg):
+    return pkg
+
+
+def _open(P, nbytes, extra=""):
+    return P.Context("cuda:devices=0,bytes=%d%s" % (nbytes, extra))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("nbytes", [4096, 16 * 1024 + 16, MiB + 48, 3 * MiB + 16 * 37, 64 * MiB])
+def test_probe_pass_bit_exact(P, nbytes, variant):
+    """Empty-ish, ragged (not a multiple of the 16 KiB tile / the CTA chunk) and larger buffers:
+    buffer contents, checksum, mismatch count and the re-keyed output all equal the oracle."""
+    n_words = nbytes // 4
+    with _open(P, nbytes) as ctx:
+        seed = oprobe.initial_seed(0)
+        for step in range(3):
+            before = ctx.probe_peek(0, 0, n_words)
+            assert np.array_equal(before, oprobe.pattern(n_words, seed))
+            (r,) = ctx.probe_health(variant=variant, min_gbs=1e-3)
+            cs, bad, first, dst = oprobe.probe_pass(before, seed, oprobe.next_seed(seed))
+            assert r.err == 0 and r.seed == seed and r.bytes == 2 * nbytes
+            assert (r.checksum, r.mismatches, r.first_bad_word) == (cs, bad, first) == (cs, 0, oprobe.NO_BAD)
+            assert r.expected_checksum == oprobe.expected_checksum(n_words, seed) == cs
+            assert r.healthy
+            assert np.array_equal(ctx.probe_peek(0, 0, n_words), dst)
+            seed = oprobe.next_seed(seed)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fault_injection_flips_health(P, variant):
+    nbytes = 8 * MiB + 16 * 5
+    n_words = nbytes // 4
+    with _open(P, nbytes) as ctx:
+        seed = oprobe.initial_seed(0)
+        (r,) = ctx.probe_health(variant=variant, min_gbs=1e-3)
+        assert r.healthy
+        seed = oprobe.next_seed(seed)
+        # corrupt three words (first tile, middle, ragged tail) of the buffer the next pass reads
+        bad_words = [5, n_words // 2 + 3, n_words - 1]
+        for w in bad_words:
+            ctx.probe_inject_fault(0, w, 0x00010000)
+        src = ctx.probe_peek(0, 0, n_words)
+        cs, bad, first, _ = oprobe.probe_pass(src, seed, oprobe.next_seed(seed))
+        (r,) = ctx.probe_health(variant=variant, min_gbs=1e-3)
+        assert (r.checksum, r.mismatches, r.first_bad_word) == (cs, 3, 5) == (cs, bad, first)
+        assert r.checksum != r.expected_checksum and not r.healthy
+        # the library re-fills after reporting: a transient fault is reported exactly once
+        seed = oprobe.next_seed(seed)
+        assert np.array_equal(ctx.probe_peek(0, 0, n_words), oprobe.pattern(n_words, seed))
+        (r,) = ctx.probe_health(variant=variant, min_gbs=1e-3)
+        assert r.healthy and r.mismatches == 0
+        # ListAndWatch reflects the verdict
+        ctx.probe_inject_fault(0, 12345, 1)
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT, min_gbs=1e-3)
+        msg = P.v1beta1.ListAndWatchResponse.FromString(wire)
+        assert [d.health for d in msg.devices] == ["Unhealthy"] and st.n_unhealthy == 1
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT, min_gbs=1e-3)
+        assert [d.health for d in P.v1beta1.ListAndWatchResponse.FromString(wire).devices] == ["Healthy"]
+
+
+def test_full_size_probe_and_bandwidth_floor(P):
+    """BASELINE.json config 2 at full size (1 GiB src -> 1 GiB dst): checksum equals the oracle's
+    closed form (size-independent property: sum of the pattern), and the stream is fast enough
+    to be a meaningful health signal.  Too-slow streams flip the verdict (min_gbs)."""
+    nbytes = 1 << 30
+    with _open(P, nbytes) as ctx:
+        seed = oprobe.initial_seed(0)
+        best = 0.0
+        for _ in range(4):
+            (r,) = ctx.probe_health()
+            assert r.err == 0 and r.mismatches == 0
+            assert r.checksum == r.expected_checksum == oprobe.expected_checksum(nbytes // 4, seed)
+            assert r.healthy
+            best = max(best, r.gbs)
+            seed = oprobe.next_seed(seed)
+        assert best > 4000.0, best
+        # spot-check the re-keyed buffer at both ends and in the middle
+        for off in (0, nbytes // 8 - 17, nbytes // 4 - 4096):
+            assert np.array_equal(ctx.probe_peek(0, off, 4096), oprobe.pattern(4096, seed, off))
+        (r,) = ctx.probe_health(min_gbs=1e9)      # impossible floor => Unhealthy, data still verified
+        assert not r.healthy and r.mismatches == 0 and r.checksum == r.expected_checksum
+
+
+def test_cuda_backend_equals_reference_algorithm_on_exported_tree(P, tmp_path):
+    """The 'equivalent fixture' contract: export what the cuda backend sees as a kfd-shaped tree;
+    the reference algorithm (oracle) on that tree must give the same device table, pair weights,
+    allocation answers, ListAndWatch list and labels as the cuda backend itself."""
+    root = str(tmp_path / "export")
+    with P.Context("cuda:bytes=%d,p2p_bytes=%d" % (64 * MiB, 32 * MiB)) as ctx:
+        devs = ctx.enumerate()
+        assert len(devs) >= 1 and list(devs) == sorted(devs)
+        ctx.export_kfd_tree(root)
+        want = oamd.GetAMDGPUs(root)
+        assert devs == want
+        for k, v in devs.items():                       # id shapes are the reference's
+            assert len(k) == 12 and k[4] == ":" and k.endswith(".0") and v["devID"] == k[:-2] + ":0"
+        # Start(): pair weights from the measured P2P matrix == oracle on the exported link files
+        assert ctx.start() == (0 if len(devs) > 1 else P._native.E_ALLOC_NO_WEIGHTS)
+        ids = sorted(devs)
+        opol = oalloc.BestEffortPolicy()
+        oerr = opol.Init(oplug.getDevices(root), root + "/sys/class/kfd/kfd/topology/nodes")
+        if len(devs) > 1:
+            assert oerr is None
+            for size in range(1, len(ids) + 1):
+                assert ctx.preferred_allocation(ids, [], size) == opol.Allocate(list(ids), [], size)[0]
+        else:
+            assert oerr is not None and not ctx.preferred_allocation_available()
+        # ListAndWatch initial list
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_INITIAL)
+        homog, lw = oplug.list_and_watch_devices(want, "gpu")
+        msg = P.v1beta1.ListAndWatchResponse.FromString(wire)
+        assert [(d.ID, d.health, d.topology.nodes[0].ID) for d in msg.devices] == lw and msg.SerializeToString() == wire
+        assert ctx.resource_list("single") == ["gpu"] == oplug.getResourceList("single", root)[0]
+        # node health: the text check on the exported tree agrees with the driver-level check
+        assert ctx.node_health() == oplug.simpleHealthCheck(root + "/sys/class/kfd/kfd") is True
+        # labels from CUDA/NVML queries == reference generators on the exported tree
+        gens = ["driver-version", "driver-src-version", "device-id", "product-name", "vram", "simd-count", "cu-count",
+                "compute-memory-partition", "compute-partitioning-supported", "memory-partitioning-supported"]
+        got = ctx.generate_labels(gens)
+        assert got == olab.generateLabels({g: True for g in gens}, root)
+        assert got["amd.com/gpu.cu-count"] == "148" and got["amd.com/gpu.product-name"] == "NVIDIA_B200"
+        # Allocate: the NVIDIA device nodes exist on the box
+        specs = ctx.device_specs(ids)
+        assert [s[0] for s in specs[:3]] == ["/dev/nvidiactl", "/dev/nvidia-uvm", "/dev/nvidia-uvm-tools"]
+        assert len(specs) == 3 + len(ids)
+        for host, cont, perm in specs:
+            assert host == cont and perm == "rw"
+            if host == "/dev/nvidiactl" or host[len("/dev/nvidia"):].isdigit():
+                assert os.path.exists(host), host
+
+
+def test_p2p_matrix(P):
+    with P.Context("cuda:bytes=%d,p2p_bytes=%d" % (256 * MiB, 256 * MiB)) as ctx:
+        n = len(ctx.enumerate())
+        gbs, lt, mm = ctx.p2p_matrix()
+        assert gbs.shape == (n, n) and (mm == 0).all()
+        for i in range(n):
+            for j in range(n):
+                if i == j:
+                    assert lt[i, j] == 0
+                else:
+                    assert lt[i, j] == oprobe.classify_link(True, float(gbs[i, j])) == 11, (i, j, gbs[i, j])
+        # probing afterwards still verifies clean (the matrix only wrote spare buffers)
+        assert all(r.healthy for r in ctx.probe_health())
+
+
+def test_multi_gpu_fanout_concurrent(P):
+    """All GPUs probed in one call: per-device seeds differ, every device verifies, and the
+    fan-out takes about one probe time, not N."""
+    with P.Context("cuda:bytes=%d" % (1 << 30)) as ctx:
+        n = len(ctx.enumerate())
+        for _ in range(3):
+            res = ctx.probe_health()
+        assert len(res) == n and len({r.seed for r in res}) == n
+        assert all(r.healthy and r.checksum == r.expected_checksum for r in res)
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT)
+        assert st.n_devices == n and st.n_unhealthy == 0
+        slowest = max(r.ms_event for r in res)
+        assert st.ms_probe < 3.0 * slowest + 1.0, (st.ms_probe, slowest)
