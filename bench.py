@@ -252,38 +252,15 @@ def main():
     warmup = max(3, args.warmup)
 
     import torch
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: the probe has no CPU fallback")
     torch.cuda.set_device(local_rank)
-
     pkg = importlib.import_module(PKG)      # raises if libb200dp.so is missing
     N = pkg._native
+    ranks = importlib.import_module(PKG + ".ranks")
+    rg = ranks.RankGroup(backend="nccl")   # barrier + timing reductions only; no data-path collective
     ctx = pkg.Context("cuda:devices=%d,bytes=%d" % (local_rank, S_BYTES))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    barrier, max_over_ranks, sum_over_ranks = rg.barrier, rg.max, rg.sum
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     windows = []
@@ -331,8 +308,7 @@ def main():
     clocks = sampler.stop(windows) if sampler else None
     if rank != 0:
         ctx.close()
-        if dist is not None:
-            dist.destroy_process_group()
+        rg.close()
         return
 
     bytes_per_step_per_gpu = 2.0 * S_BYTES
@@ -370,8 +346,7 @@ def main():
                                 "kfd_walk_stream_start_ms": round(start_ms, 4), "kfd_walk_heartbeat_ms": round(beat_ms, 4)}
     print(json.dumps(line))
     ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    rg.close()
 
 
 if __name__ == "__main__":
