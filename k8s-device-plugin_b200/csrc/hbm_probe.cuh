@@ -262,6 +262,22 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// L2 cache-policy variants: the probe streams every byte exactly once, so both directions
+// can be marked evict-first to keep the 126 MB L2 from retaining dead lines.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                              uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
@@ -289,7 +305,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Driver, tile k: wait done[slot k] -> bulk store slot k -> wait until the store of
 // tile k-1 has finished READING smem -> bulk load tile k-1+STAGES into that slot.
 // TILE_VEC: vectors (16 B) per tile. Dynamic smem = STAGES*TILE_VEC*16 + 2*STAGES*8.
-template <int CW, int TILE_VEC, int STAGES>
+template <int CW, int TILE_VEC, int STAGES, int HINT = 0>
 __global__ void __launch_bounds__((CW + 1) * 32)
 hbm_probe_tma(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned long long n_vec,
               uint32_t seed, uint32_t delta, ProbeCtl* ctl, ProbeOut* out, unsigned long long seq) {
@@ -320,17 +336,20 @@ hbm_probe_tma(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned l
     Acc a;
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
+            const uint64_t pol = HINT ? policy_evict_first() : 0ull;
             for (int k = 0; k < STAGES && (unsigned long long)k < my_tiles; ++k) {
                 const unsigned long long t = blockIdx.x + (unsigned long long)k * gridDim.x;
                 mbar_expect_tx(&full[k], TILE_BYTES);
-                bulk_g2s(tiles + (size_t)k * TILE_VEC, src + t * TILE_VEC, TILE_BYTES, &full[k]);
+                if (HINT & 1) bulk_g2s_hint(tiles + (size_t)k * TILE_VEC, src + t * TILE_VEC, TILE_BYTES, &full[k], pol);
+                else bulk_g2s(tiles + (size_t)k * TILE_VEC, src + t * TILE_VEC, TILE_BYTES, &full[k]);
             }
             for (unsigned long long k = 0; k < my_tiles; ++k) {
                 const int slot = (int)(k % STAGES);
                 const uint32_t parity = (uint32_t)((k / STAGES) & 1);
                 const unsigned long long t = blockIdx.x + k * gridDim.x;
                 mbar_wait(&done[slot], parity);
-                bulk_s2g(dst + t * TILE_VEC, tiles + (size_t)slot * TILE_VEC, TILE_BYTES);
+                if (HINT & 2) bulk_s2g_hint(dst + t * TILE_VEC, tiles + (size_t)slot * TILE_VEC, TILE_BYTES, pol);
+                else bulk_s2g(dst + t * TILE_VEC, tiles + (size_t)slot * TILE_VEC, TILE_BYTES);
                 bulk_commit();
                 if (k >= 1) {
                     const unsigned long long kn = k - 1 + STAGES;
@@ -339,7 +358,8 @@ hbm_probe_tma(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned l
                         const int sn = (int)(kn % STAGES);
                         const unsigned long long tn = blockIdx.x + kn * gridDim.x;
                         mbar_expect_tx(&full[sn], TILE_BYTES);
-                        bulk_g2s(tiles + (size_t)sn * TILE_VEC, src + tn * TILE_VEC, TILE_BYTES, &full[sn]);
+                        if (HINT & 1) bulk_g2s_hint(tiles + (size_t)sn * TILE_VEC, src + tn * TILE_VEC, TILE_BYTES, &full[sn], pol);
+                        else bulk_g2s(tiles + (size_t)sn * TILE_VEC, src + tn * TILE_VEC, TILE_BYTES, &full[sn]);
                     }
                 }
             }

@@ -103,6 +103,17 @@ def test_full_size_probe_and_bandwidth_floor(P):
         assert not r.healthy and r.mismatches == 0 and r.checksum == r.expected_checksum
 
 
+def test_full_size_golden_checksums(P):
+    """1 GiB passes against the committed golden checksums (tests/golden/probe_vectors.json)."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "probe_vectors.json")))
+    seeds = g["full_size"]["seeds"]
+    with _open(P, g["full_size"]["n_words"] * 4) as ctx:
+        for seed_s, want in seeds.items():
+            (r,) = ctx.probe_health()
+            assert r.seed == int(seed_s) and r.checksum == want == r.expected_checksum and r.mismatches == 0
+
+
 def test_cuda_backend_equals_reference_algorithm_on_exported_tree(P, tmp_path):
     """The 'equivalent fixture' contract: export what the cuda backend sees as a kfd-shaped tree;
     the reference algorithm (oracle) on that tree must give the same device table, pair weights,

@@ -91,3 +91,20 @@ def test_probe_fixed_vectors():
     assert cs & oprobe.NO_BAD == oprobe.expected_checksum(n, seed)
     assert oprobe.classify_link(True, 700.0) == 11 and oprobe.classify_link(True, 50.0) == 2
     assert oprobe.classify_link(False, 700.0) == 0
+
+
+def test_probe_golden_vectors():
+    """Frozen known answers for the probe specification (tests/golden/probe_vectors.json)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "probe_vectors.json")))
+    for c in g["cases"]:
+        assert oprobe.initial_seed(c["device"]) == c["seed"] and oprobe.next_seed(c["seed"]) == c["next_seed"]
+        src = oprobe.pattern(c["n_words"], c["seed"])
+        cs, bad, first, dst = oprobe.probe_pass(src, c["seed"], c["next_seed"])
+        assert (cs, bad, first) == (c["checksum"], 0, oprobe.NO_BAD)
+        assert [int(x) for x in src[:4]] == c["head"] and [int(x) for x in src[-2:]] == c["tail"]
+        assert [int(x) for x in dst[:4]] == c["dst_head"] and oprobe.checksum(dst) == c["dst_checksum"]
+        assert np.array_equal(dst, oprobe.pattern(c["n_words"], c["next_seed"]))
+    seed, want = next(iter(g["full_size"]["seeds"].items()))
+    assert oprobe.expected_checksum(g["full_size"]["n_words"], int(seed)) == want

@@ -41,12 +41,12 @@ template <int T, int U> static void launch_r256(const uint4* s, uint4* d, unsign
     uint32_t delta, ProbeCtl* c, ProbeOut* o, unsigned long long seq, int grid, cudaStream_t st) {
     hbm_probe_r256<T, U><<<grid, T, 0, st>>>(s, d, n, seed, delta, c, o, seq);
 }
-template <int CW, int TV, int ST> static void launch_tma(const uint4* s, uint4* d, unsigned long long n, uint32_t seed,
+template <int CW, int TV, int ST, int HINT = 0> static void launch_tma(const uint4* s, uint4* d, unsigned long long n, uint32_t seed,
     uint32_t delta, ProbeCtl* c, ProbeOut* o, unsigned long long seq, int grid, cudaStream_t st) {
     constexpr size_t smem = (size_t)ST * TV * 16 + 2 * ST * 8;
     static bool once = false;
-    if (!once) { CK(cudaFuncSetAttribute(hbm_probe_tma<CW, TV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
-    hbm_probe_tma<CW, TV, ST><<<grid, (CW + 1) * 32, smem, st>>>(s, d, n, seed, delta, c, o, seq);
+    if (!once) { CK(cudaFuncSetAttribute(hbm_probe_tma<CW, TV, ST, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
+    hbm_probe_tma<CW, TV, ST, HINT><<<grid, (CW + 1) * 32, smem, st>>>(s, d, n, seed, delta, c, o, seq);
 }
 
 __global__ void plain_copy(const uint4* __restrict__ s, uint4* __restrict__ d, unsigned long long n) {
@@ -90,6 +90,11 @@ int main(int argc, char** argv) {
         cfgs.push_back({"tma_cw" #CW "_tv" #TV "_st" #ST, launch_tma<CW, TV, ST>, k});
     R128(256, 2) R128(256, 4) R128(256, 8) R128(512, 2) R128(512, 4) R128(512, 8) R128(1024, 2) R128(1024, 4)
     R256(256, 1) R256(256, 2) R256(256, 4) R256(512, 1) R256(512, 2) R256(512, 4)
+#define TMAH(CW, TV, ST, H) for (int k : {1, 2, 3}) if ((size_t)k * ((size_t)ST * TV * 16 + 1024) <= 227 * 1024 && k * (CW + 1) * 32 <= 2048) \
+        cfgs.push_back({"tmah" #H "_cw" #CW "_tv" #TV "_st" #ST, launch_tma<CW, TV, ST, H>, k});
+    TMAH(4, 1024, 3, 1) TMAH(4, 1024, 3, 2) TMAH(4, 1024, 3, 3) TMAH(4, 512, 6, 3) TMAH(4, 768, 4, 0) TMAH(4, 768, 4, 3)
+    TMAH(8, 1024, 3, 0) TMAH(8, 1024, 3, 3) TMAH(2, 1024, 3, 0) TMAH(4, 512, 6, 0) TMAH(4, 1536, 3, 0) TMAH(4, 1280, 3, 0)
+    TMAH(4, 896, 3, 0) TMAH(4, 640, 5, 0) TMAH(4, 1024, 4, 3) TMAH(6, 768, 4, 0) TMAH(6, 1536, 3, 0)
     TMA(4, 512, 4) TMA(4, 1024, 3) TMA(4, 1024, 4) TMA(4, 1024, 6) TMA(4, 2048, 3) TMA(4, 2048, 4)
     TMA(8, 1024, 4) TMA(8, 2048, 3) TMA(8, 2048, 4) TMA(8, 4096, 3) TMA(2, 1024, 4) TMA(2, 512, 6)
 
