@@ -163,6 +163,9 @@ typedef struct b2dp_probe_opts {
 #define B2DP_PROBE_VARIANT_TMA 0u        /* smem-staged bulk-copy kernel (default) */
 #define B2DP_PROBE_VARIANT_R128 1u       /* register-path kernel (for A/B measurement) */
 #define B2DP_PROBE_VARIANT_MASK 0xfu
+#define B2DP_PROBE_VIA_WORKERS 0x10u     /* launch + wait on each GPU's own worker thread (full isolation from a
+                                            wedged driver call) instead of the default low-latency path where the
+                                            calling thread enqueues on every stream and polls the events */
 
 typedef struct b2dp_probe_result {
     int32_t device;             /* index into b2dp_enumerate() order */
@@ -211,7 +214,9 @@ typedef struct b2dp_cycle_opts {
     int32_t reserved;
 } b2dp_cycle_opts;
 #define B2DP_LW_INITIAL 0x1u         /* stream start: enumerate, every device "Healthy" (plugin.go:231-299) */
-#define B2DP_LW_HEARTBEAT 0x2u       /* heartbeat tick: node health + per-device health + re-send (plugin.go:304-320) */
+#define B2DP_LW_HEARTBEAT 0x2u       /* heartbeat tick: node health + per-device health + re-send (plugin.go:304-320);
+                                        reuses the device list of the last INITIAL call (the reference builds the
+                                        list once per stream), enumerating only if there has been none */
 #define B2DP_LW_EXTERNAL_SOURCE 0x4u /* merge src_* instead of running the GPU probe */
 #define B2DP_LW_NO_PROBE 0x8u        /* heartbeat without a per-device source: default health only */
 

@@ -33,6 +33,7 @@ E_ALLOC_INIT, E_ALLOC_NOCANDIDATE, E_ALLOC_EMPTY_DEVICES, E_ALLOC_NO_WEIGHTS = -
 E_ALLOC_SUBSET_SIZE, E_ALLOC_SUBSET_AVAIL = -28, -29
 
 PROBE_VARIANT_TMA, PROBE_VARIANT_R128 = 0, 1
+PROBE_VIA_WORKERS = 0x10
 LW_INITIAL, LW_HEARTBEAT, LW_EXTERNAL_SOURCE, LW_NO_PROBE = 1, 2, 4, 8
 
 Id64 = C.c_char * 64

@@ -106,8 +106,8 @@ class Context:
         N.check(N.lib.b2dp_node_health(self._h, C.byref(v)), self._h)
         return bool(v.value)
 
-    def probe_health(self, timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0) -> List[ProbeResult]:
-        opts = N.ProbeOpts(timeout_ms, variant, min_gbs, 0)
+    def probe_health(self, timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0, via_workers=False) -> List[ProbeResult]:
+        opts = N.ProbeOpts(timeout_ms, variant | (N.PROBE_VIA_WORKERS if via_workers else 0), min_gbs, 0)
         rc, arr, n = N.grow_call(lambda cap: (N.ProbeResult * cap)(),
                                  lambda a, cap, pn: N.lib.b2dp_probe_health(self._h, C.byref(opts), a, cap, pn))
         N.check(rc, self._h)

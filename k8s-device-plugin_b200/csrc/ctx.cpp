@@ -37,6 +37,8 @@ struct b2dp_ctx {
     std::vector<Link> links;    // cuda: measured link list (node ids), filled by the p2p matrix
     bool have_links = false;
     std::vector<float> p2p_gbs; // last matrix, n x n
+    std::vector<Device> stream_devs;  // the device list of the current ListAndWatch stream
+    bool have_stream_devs = false;
 };
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
@@ -293,11 +295,23 @@ extern "C" int b2dp_list_and_watch(b2dp_ctx* c, const char* resource, const b2dp
     const bool heartbeat = (flags & B2DP_LW_HEARTBEAT) != 0;
     *len = 0;
 
-    // plugin.go:231-237: GetAMDGPUs + IsHomogeneous (the reference enumerates twice; one
-    // enumeration serves both here)
+    // plugin.go:231-237: GetAMDGPUs + IsHomogeneous at stream start (the reference enumerates
+    // twice; one enumeration serves both here).  The device list is built ONCE per stream
+    // (plugin.go:235-299) and only re-sent with new health on a heartbeat (plugin.go:304-320),
+    // so a heartbeat reuses the list of the last INITIAL call.
     std::vector<Device> devs;
-    int rc = enumerate_ctx(c, devs);
-    if (rc != B2DP_OK) return rc;
+    int rc = B2DP_OK;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (heartbeat && c->have_stream_devs) devs = c->stream_devs;
+    }
+    if (devs.empty()) {
+        rc = enumerate_ctx(c, devs);
+        if (rc != B2DP_OK) return rc;
+        std::lock_guard<std::mutex> g(c->mu);
+        c->stream_devs = devs;
+        c->have_stream_devs = true;
+    }
     const bool homogeneous = partition_histogram(devs).size() <= 1;
     st.homogeneous = homogeneous;
     const double t1 = now_ms();

@@ -115,6 +115,7 @@ struct Gpu {
     uint32_t seed = 0;
     int cur = 0;
     unsigned long long seq = 0;
+    std::atomic<bool> inflight{false};  // a timed-out pass is still owned by the worker
     std::vector<char> peer_enabled;
 };
 
@@ -393,6 +394,7 @@ struct ProbeJobResult {
     ProbeOut out{};
     float ms = 0;
     uint32_t seed = 0;
+    unsigned long long seq = 0;
     bool seq_ok = false;
 };
 
@@ -407,6 +409,35 @@ static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uin
                                                                                     g->ctl, g->out_d, seq);
 }
 
+// Enqueue one pass on g's stream (caller must have made g's device current).
+static void probe_issue(Gpu* g, ProbeJobResult* r, unsigned long long n_vec, uint32_t variant) {
+    const uint32_t seed = g->seed, next = seed * 1664525u + 1013904223u;
+    r->seed = seed;
+    r->seq = ++g->seq;
+    cudaEventRecord(g->e0, g->stream);
+    launch_probe(g, n_vec, variant, seed, seed ^ next, g->buf[g->cur], g->buf[g->cur ^ 1], r->seq);
+    r->ce = cudaGetLastError();
+    cudaEventRecord(g->e1, g->stream);
+}
+
+// After e1 completed: read the published result, advance the seed / ping-pong state.
+static void probe_collect(Gpu* g, ProbeJobResult* r, unsigned long long n_vec) {
+    cudaError_t e = r->ce;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&r->ms, g->e0, g->e1);
+    r->ce = e;
+    if (e != cudaSuccess) return;
+    memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // published before the event fired
+    r->seq_ok = r->out.seq == r->seq;
+    g->seed = g->seed * 1664525u + 1013904223u;
+    g->cur ^= 1;
+    if (r->out.mismatches != 0 || !r->seq_ok) {
+        // report once, then start the next pass from a clean pattern: a transient flip is
+        // reported exactly once, a stuck cell shows up again on the next pass
+        hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
+        cudaStreamSynchronize(g->stream);
+    }
+}
+
 int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_probe_result>& out, std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
     const unsigned long long n_vec = be->n_vec(), n_words = n_vec * 4;
@@ -414,47 +445,79 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     int rc = get_bitcounts(be, n_words, bc, err);
     if (rc != B2DP_OK) return rc;
     const uint32_t variant = opts ? (opts->flags & B2DP_PROBE_VARIANT_MASK) : 0;
+    const bool via_workers = opts && (opts->flags & B2DP_PROBE_VIA_WORKERS);
     const uint32_t timeout_ms = opts && opts->timeout_ms ? opts->timeout_ms : 5000;  // health.go:37
     const float min_gbs = opts && opts->min_gbs > 0 ? opts->min_gbs : be->cfg.min_gbs;
     const size_t n = be->gpus.size();
     std::vector<std::shared_ptr<ProbeJobResult>> res(n);
     std::vector<std::shared_ptr<Completion>> cs(n);
+    std::vector<char> state(n, 0);  // 0 pending, 1 done, 2 timed out / busy
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
-    for (size_t i = 0; i < n; ++i) {  // launch everywhere before waiting anywhere
-        Gpu* g = be->gpus[i].get();
-        auto r = std::make_shared<ProbeJobResult>();
-        res[i] = r;
-        cs[i] = post(g, [g, r, n_vec, variant] {
-            const uint32_t seed = g->seed, next = seed * 1664525u + 1013904223u;
-            const unsigned long long seq = ++g->seq;
-            r->seed = seed;
-            cudaEventRecord(g->e0, g->stream);
-            launch_probe(g, n_vec, variant, seed, seed ^ next, g->buf[g->cur], g->buf[g->cur ^ 1], seq);
-            cudaError_t e = cudaGetLastError();
-            cudaEventRecord(g->e1, g->stream);
-            if (e == cudaSuccess) e = cudaEventSynchronize(g->e1);
-            if (e == cudaSuccess) e = cudaEventElapsedTime(&r->ms, g->e0, g->e1);
-            r->ce = e;
-            if (e != cudaSuccess) return;
-            memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // published before the event fired
-            r->seq_ok = r->out.seq == seq;
-            g->seed = next;
-            g->cur ^= 1;
-            if (r->out.mismatches != 0 || !r->seq_ok) {
-                // report once, then start the next pass from a clean pattern: a transient flip is
-                // reported exactly once, a stuck cell shows up again on the next pass
-                hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
-                cudaStreamSynchronize(g->stream);
+    for (size_t i = 0; i < n; ++i) res[i] = std::make_shared<ProbeJobResult>();
+
+    if (via_workers) {
+        // fully isolated path: each GPU's own thread launches and waits; a wedged driver call can
+        // only ever block that worker
+        for (size_t i = 0; i < n; ++i) {  // launch everywhere before waiting anywhere
+            Gpu* g = be->gpus[i].get();
+            auto r = res[i];
+            if (g->inflight.load()) { state[i] = 2; continue; }
+            cs[i] = post(g, [g, r, n_vec, variant] {
+                probe_issue(g, r.get(), n_vec, variant);
+                if (r->ce == cudaSuccess) r->ce = cudaEventSynchronize(g->e1);
+                probe_collect(g, r.get(), n_vec);
+            });
+        }
+        for (size_t i = 0; i < n; ++i)
+            if (state[i] == 0) state[i] = cs[i]->wait_until(deadline) ? 1 : 2;
+    } else {
+        // low-latency path (default): the calling thread enqueues on every GPU's stream, then polls
+        // the completion events; no thread hand-offs on the critical path.  A device that misses
+        // the deadline is handed to its worker to be collected whenever it finishes.
+        for (size_t i = 0; i < n; ++i) {
+            Gpu* g = be->gpus[i].get();
+            if (g->inflight.load()) { state[i] = 2; continue; }
+            cudaSetDevice(g->ordinal);
+            probe_issue(g, res[i].get(), n_vec, variant);
+        }
+        size_t pending = 0;
+        for (size_t i = 0; i < n; ++i) pending += state[i] == 0;
+        unsigned spins = 0;
+        while (pending) {
+            for (size_t i = 0; i < n; ++i) {
+                if (state[i] != 0) continue;
+                Gpu* g = be->gpus[i].get();
+                cudaError_t q = res[i]->ce != cudaSuccess ? res[i]->ce : cudaEventQuery(g->e1);
+                if (q == cudaErrorNotReady) continue;
+                if (q != cudaSuccess) res[i]->ce = q;
+                cudaSetDevice(g->ordinal);
+                probe_collect(g, res[i].get(), n_vec);
+                state[i] = 1;
+                --pending;
             }
-        });
+            if (pending && (++spins & 0xff) == 0 && std::chrono::steady_clock::now() > deadline) break;
+        }
+        for (size_t i = 0; i < n; ++i) {
+            if (state[i] != 0) continue;
+            state[i] = 2;
+            Gpu* g = be->gpus[i].get();
+            auto r = res[i];
+            g->inflight.store(true);
+            post(g, [g, r, n_vec] {
+                if (r->ce == cudaSuccess) r->ce = cudaEventSynchronize(g->e1);
+                probe_collect(g, r.get(), n_vec);
+                g->inflight.store(false);
+            });
+        }
     }
+
     out.assign(n, b2dp_probe_result{});
     for (size_t i = 0; i < n; ++i) {
         b2dp_probe_result& o = out[i];
         o.device = (int)i;
         o.bytes = 2ull * be->cfg.bytes;
         o.first_bad_word = ~0ull;
-        if (!cs[i]->wait_until(deadline)) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; continue; }
+        if (state[i] == 2) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; continue; }
         const ProbeJobResult& r = *res[i];
         o.seed = r.seed;
         o.expected_checksum = expected_checksum(bc, n_words, r.seed);
@@ -481,6 +544,7 @@ static Gpu* gpu_at(CudaBackend* be, int device, std::string& err) {
 }
 
 int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask, std::string& err) {
+    std::lock_guard<std::mutex> pl(be->probe_mu);
     Gpu* g = gpu_at(be, device, err);
     if (!g) return B2DP_E_INVAL;
     if (word >= be->n_vec() * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
@@ -494,6 +558,7 @@ int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask,
 }
 
 int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
+    std::lock_guard<std::mutex> pl(be->probe_mu);
     const unsigned long long n_vec = be->n_vec();
     for (int i = 0; i < (int)be->gpus.size(); ++i) {
         if (device >= 0 && device != i) continue;
@@ -510,6 +575,7 @@ int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
 }
 
 int cuda_probe_peek(CudaBackend* be, int device, uint64_t word, uint32_t* out, uint64_t n, std::string& err) {
+    std::lock_guard<std::mutex> pl(be->probe_mu);
     Gpu* g = gpu_at(be, device, err);
     if (!g) return B2DP_E_INVAL;
     if (word + n > be->n_vec() * 4) { err = "range out of bounds"; return B2DP_E_INVAL; }

@@ -123,6 +123,22 @@ inline std::vector<std::string> glob_node_properties(const std::string& topo_roo
     return out;
 }
 
+// Same match set and order, visited lazily: fn(path) returns false to stop early (the health
+// check returns at the first GPU node, so only the files actually consumed are stat'ed).
+template <class F>
+inline void for_each_node_properties(const std::string& topo_root, F&& fn) {
+    const std::string nodes = topo_root + "/topology/nodes";
+    std::vector<std::string> names;
+    if (!is_dir(nodes) || !list_dir_sorted(nodes, names)) return;
+    for (const auto& n : names) {
+        const std::string nd = nodes + "/" + n;
+        if (!is_dir(nd)) continue;
+        const std::string p = nd + "/properties";
+        if (!lexists(p)) continue;
+        if (!fn(p)) return;
+    }
+}
+
 // ---- bufio.Scanner -------------------------------------------------------------------
 constexpr size_t kMaxScanToken = 64 * 1024;
 

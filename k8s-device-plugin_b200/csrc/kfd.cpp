@@ -214,8 +214,9 @@ int kfd_count_gpu_dev(const std::string& topo_root) {
 
 bool kfd_simple_health_check(const std::string& topo_root) {
     std::string data;  // plugin.go:161-206
-    for (const auto& f : go::glob_node_properties(topo_root)) {
-        if (!go::read_file(f, data)) continue;
+    bool found = false;
+    go::for_each_node_properties(topo_root, [&](const std::string& f) {
+        if (!go::read_file(f, data)) return true;
         int64_t cpu_cores = 0, gfx = 0;
         auto starts = [](std::string_view l, const char* p) { return l.compare(0, strlen(p), p) == 0; };
         const bool scan_err = go::scan_lines(data, [&](std::string_view line) {
@@ -228,10 +229,11 @@ bool kfd_simple_health_check(const std::string& topo_root) {
             }
             return true;
         });
-        if (scan_err) continue;  // plugin.go:193-196
-        if (cpu_cores == 0 && gfx > 0) return true;
-    }
-    return false;
+        if (scan_err) return true;  // plugin.go:193-196
+        if (cpu_cores == 0 && gfx > 0) { found = true; return false; }  // first hit wins
+        return true;
+    });
+    return found;
 }
 
 }  // namespace b2dp

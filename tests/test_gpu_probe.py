@@ -103,6 +103,23 @@ def test_full_size_probe_and_bandwidth_floor(P):
         assert not r.healthy and r.mismatches == 0 and r.checksum == r.expected_checksum
 
 
+def test_worker_path_equals_direct_path(P):
+    """B2DP_PROBE_VIA_WORKERS (per-GPU worker threads launch and wait) and the default low-latency
+    path (caller enqueues, polls events) drive the same state machine: interleave them."""
+    nbytes = 16 * MiB + 16
+    with _open(P, nbytes) as ctx:
+        seed = oprobe.initial_seed(0)
+        for step in range(6):
+            (r,) = ctx.probe_health(min_gbs=1e-3, via_workers=bool(step % 2), variant=step % 2)
+            assert r.seed == seed and r.healthy and r.checksum == oprobe.expected_checksum(nbytes // 4, seed)
+            seed = oprobe.next_seed(seed)
+        ctx.probe_inject_fault(0, 99, 2)
+        (r,) = ctx.probe_health(min_gbs=1e-3, via_workers=True)
+        assert (r.mismatches, r.first_bad_word, r.healthy) == (1, 99, False)
+        (r,) = ctx.probe_health(min_gbs=1e-3)
+        assert r.healthy
+
+
 def test_full_size_golden_checksums(P):
     """1 GiB passes against the committed golden checksums (tests/golden/probe_vectors.json)."""
     import json
