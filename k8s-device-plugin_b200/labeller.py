@@ -47,3 +47,13 @@ def removeOldNodeLabels(labels: Optional[Dict[str, str]]) -> Optional[Dict[str, 
 def generateLabels(ctx: Context, lblProps: Dict[str, bool]) -> Dict[str, str]:
     """main.go:383-397: `lblProps` = the labeller's bool flags."""
     return ctx.generate_labels([k for k, v in lblProps.items() if v])
+
+
+def Reconcile(node_labels: Optional[Dict[str, str]], labels: Dict[str, str]) -> Dict[str, str]:
+    """controller.go:23-58 on the node's label map (the K8s client Get/Update around it is the
+    caller's job): nil map -> {}, remove this labeller's old labels, set the generated ones."""
+    if node_labels is None:
+        node_labels = {}
+    removeOldNodeLabels(node_labels)
+    node_labels.update(labels)
+    return node_labels

@@ -404,3 +404,36 @@ def test_synthetic_b200_tree(P, tmp_path):
         got = ctx.enumerate()
         assert got == oamd.GetAMDGPUs(root2) and len(got) == 56 == len(ids2)
         assert ctx.resource_list("mixed") == ["1g_23gb"]
+
+
+# main_test.go:59-125, both cases verbatim, through the ABI and the oracle
+REMOVE_OLD_CASES = [
+    ({"amd.com/gpu.cu-count": "104", "amd.com/gpu.device-id": "740f", "amd.com/gpu.driver-version": "6.10.5",
+      "amd.com/gpu.family": "AI", "amd.com/gpu.product-name": "Instinct_MI210", "amd.com/gpu.simd-count": "416",
+      "amd.com/gpu.vram": "64G", "beta.amd.com/gpu.cu-count": "104", "beta.amd.com/gpu.cu-count.104": "1",
+      "beta.amd.com/gpu.device-id": "740f", "beta.amd.com/gpu.device-id.740f": "1", "beta.amd.com/gpu.family": "HPC",
+      "beta.amd.com/gpu.family.HPC": "1", "beta.amd.com/gpu.product-name": "Instinct_MI300X",
+      "beta.amd.com/gpu.product-name.Instinct_MI300X": "1", "beta.amd.com/gpu.simd-count": "416",
+      "beta.amd.com/gpu.simd-count.416": "1", "beta.amd.com/gpu.vram": "64G", "beta.amd.com/gpu.vram.64G": "1",
+      "dummyLabel1": "1", "dummyLabel2": "2"},
+     {"dummyLabel1": "1", "dummyLabel2": "2"}),
+    ({"amd.com/cpu": "true", "amd.com/gpu": "true", "amd.com/mi300x": "true", "dummyLabel1": "1", "dummyLabel2": "2"},
+     {"amd.com/cpu": "true", "amd.com/gpu": "true", "amd.com/mi300x": "true", "dummyLabel1": "1", "dummyLabel2": "2"}),
+]
+
+
+@pytest.mark.parametrize("labels,expect", REMOVE_OLD_CASES)
+def test_remove_old_node_labels_reference_cases(P, labels, expect):
+    assert olab.removeOldNodeLabels(dict(labels)) == expect
+    assert P.labeller.removeOldNodeLabels(dict(labels)) == expect
+
+
+def test_reconcile(P, kfd, tmp_path):
+    """controller.go:23-58: stale labels of this labeller vanish, foreign labels stay, new ones land."""
+    root = fake_sysfs.build(str(tmp_path / "r"), topo_dir(kfd, "mi210"))
+    with P.Context("kfd:" + root) as ctx:
+        new = P.labeller.generateLabels(ctx, {"vram": True, "cu-count": True, "device-id": True})
+    node = dict(REMOVE_OLD_CASES[0][0])
+    got = P.labeller.Reconcile(node, new)
+    assert got == {**REMOVE_OLD_CASES[0][1], **new} and "beta.amd.com/gpu.family.HPC" not in got
+    assert P.labeller.Reconcile(None, new) == new
