@@ -28,3 +28,13 @@ def kfd():
 def pkg():
     """The product package; its directory name has a hyphen, so import by string."""
     return importlib.import_module("k8s-device-plugin_b200")
+
+
+@pytest.fixture
+def short_dir():
+    """A short scratch dir for unix sockets (sun_path is limited to 107 chars)."""
+    import shutil
+    import tempfile
+    d = tempfile.mkdtemp(prefix="b2s_", dir="/tmp")
+    yield d
+    shutil.rmtree(d, ignore_errors=True)

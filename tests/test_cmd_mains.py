@@ -40,13 +40,12 @@ def test_device_plugin_main_bad_strategy(pkg, capsys):
     assert "invalid resource naming strategy: both" in capsys.readouterr().err
 
 
-def test_device_plugin_main_registers_and_beats(pkg, kfd, tmp_path):
+def test_device_plugin_main_registers_and_beats(pkg, kfd, tmp_path, short_dir):
     dp = importlib.import_module("k8s-device-plugin_b200.cmd_device_plugin")
     V = pkg.v1beta1
     root = fake_sysfs.build(str(tmp_path / "r"), topo_dir(kfd, "mi308"), compute="cpx", memory="nps1",
                             hetero_second=("spx", "nps1"))
-    plug_dir = str(tmp_path / "dp")
-    os.makedirs(plug_dir)
+    plug_dir = short_dir
     kubelet = FakeKubelet(os.path.join(plug_dir, "kubelet.sock"), V)
     rc = {}
 

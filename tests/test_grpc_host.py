@@ -44,12 +44,11 @@ def _call(ch, method, req, resp_cls):
                           response_deserializer=resp_cls.FromString)(req, timeout=10)
 
 
-def test_kubelet_round_trip(pkg, kfd, tmp_path):
+def test_kubelet_round_trip(pkg, kfd, tmp_path, short_dir):
     srv_mod = importlib.import_module("k8s-device-plugin_b200.server")
     V = pkg.v1beta1
     root = fake_sysfs.build(str(tmp_path / "r"), topo_dir(kfd, "cpx"), compute="cpx", memory="nps4")
-    plug_dir = str(tmp_path / "dp")
-    os.makedirs(plug_dir)
+    plug_dir = short_dir
     kubelet = FakeKubelet(os.path.join(plug_dir, "kubelet.sock"), V)
     gpus = oamd.GetAMDGPUs(root)
     ids = sorted(gpus)
