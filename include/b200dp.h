@@ -290,11 +290,12 @@ B2DP_API int b2dp_preferred_allocation(b2dp_ctx *ctx, const char *const *availab
 typedef struct b2dp_p2p_opts {
     uint64_t bytes;      /* per directed pair; 0 = context default (256 MiB) */
     uint32_t iters;      /* timed repetitions per pair, best kept; 0 = 2 */
-    uint32_t flags;
+    uint32_t flags;      /* B2DP_P2P_* */
 } b2dp_p2p_opts;
-/* For every ordered pair (i != j) a kernel on GPU i reads a peer-mapped buffer on GPU j
- * (LDG.128 over NVLink) into local HBM, verifying the pattern; pairs run in N-1 rounds of
- * disjoint matchings.  gbs and link_type are N x N row-major ([i*N + j]: i reads from j);
+#define B2DP_P2P_BIDIR 0x1u /* run both directions of a pair concurrently (default: one direction at a time) */
+/* For every ordered pair (i != j) a kernel on GPU i pulls a peer-mapped buffer on GPU j over
+ * NVLink (bulk copies into shared memory) into local HBM, verifying the pattern on receipt;
+ * pairs run in N-1 rounds of disjoint matchings, one direction per half-round.  gbs and link_type are N x N row-major ([i*N + j]: i reads from j);
  * diagonal = local HBM copy GB/s and type 0.  link_type: 11 NVLink-class, 2 PCIe-class,
  * 0 no peer access (oracle/probe.py classify_link).  `n` must equal the device count. */
 B2DP_API int b2dp_p2p_matrix(b2dp_ctx *ctx, const b2dp_p2p_opts *opts, float *gbs, int32_t *link_type, uint64_t *mismatches, int n);

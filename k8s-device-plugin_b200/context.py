@@ -194,13 +194,13 @@ class Context:
         return [N.s(out[i].value) for i in range(n.value)]
 
     # ---- P2P / export / labels -------------------------------------------------------------
-    def p2p_matrix(self, bytes_per_pair: int = 0, iters: int = 0):
+    def p2p_matrix(self, bytes_per_pair: int = 0, iters: int = 0, bidir: bool = False):
         import numpy as np
         arr, n = self.enumerate_raw()
         gbs = np.zeros((n, n), dtype=np.float32)
         lt = np.zeros((n, n), dtype=np.int32)
         mm = np.zeros((n, n), dtype=np.uint64)
-        opts = N.P2pOpts(bytes_per_pair, iters, 0)
+        opts = N.P2pOpts(bytes_per_pair, iters, 1 if bidir else 0)
         N.check(N.lib.b2dp_p2p_matrix(self._h, C.byref(opts), gbs.ctypes.data_as(C.POINTER(C.c_float)),
                                       lt.ctypes.data_as(C.POINTER(C.c_int32)),
                                       mm.ctypes.data_as(C.POINTER(C.c_uint64)), n), self._h)

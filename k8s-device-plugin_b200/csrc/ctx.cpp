@@ -536,6 +536,18 @@ extern "C" int b2dp_generate_labels(b2dp_ctx* c, const char* enabled, b2dp_label
     if (rc != B2DP_OK) return rc;
     LabelSource src;
     label_source(c, src);
+    if (c->kind == b2dp_ctx::CUDA && strstr(enabled, "p2p-link")) {
+        // extension label: interconnect class per GPU = the weakest link class to any peer
+        std::lock_guard<std::mutex> g(c->mu);
+        rc = ensure_links(c, devs);
+        if (rc != B2DP_OK) return rc;
+        for (const auto& d : devs) {
+            int worst = 11, peers = 0;
+            for (const auto& l : c->links)
+                if (l.from == d.node_id) { ++peers; if (l.type != 11) worst = l.type == 2 && worst != 0 ? 2 : 0; }
+            src.p2p_class.push_back(!peers || worst == 0 ? "none" : worst == 2 ? "pcie" : "nvlink");
+        }
+    }
     std::map<std::string, std::string> m;
     rc = generate_labels(devs, src, enabled, m);
     if (rc != B2DP_OK) return rc;

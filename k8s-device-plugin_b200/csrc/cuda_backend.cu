@@ -37,7 +37,6 @@ constexpr int kTmaStages = 3;
 constexpr int kTmaCtasPerSm = 2;    // 2 x 3 x 16 KiB = 96 KiB staged per SM
 constexpr size_t kTmaSmem = (size_t)kTmaStages * kTmaTileVec * 16 + 2 * kTmaStages * 8;
 constexpr int kRegThreads = 512, kRegUnroll = 2, kRegCtasPerSm = 2;
-constexpr int kP2pThreads = 512, kP2pUnroll = 4, kP2pCtasPerSm = 4;
 
 // bit b of (uint32(i) * K) summed over i < n_words, for the closed-form checksum
 __global__ void pattern_bit_counts(unsigned long long n_words, unsigned long long* counts /*[32]*/) {
@@ -639,8 +638,11 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
             for (int it = 0; it < iters + 1; ++it) {  // first iteration is a warm-up
                 const unsigned long long seq = ++g->seq;
                 cudaEventRecord(g->e0, g->stream);
-                hbm_probe_r128<kP2pThreads, kP2pUnroll><<<(int)g->sms * kP2pCtasPerSm, kP2pThreads, 0, g->stream>>>(
-                    src, g->buf[g->cur ^ 1], n_vec, seed, 0u, g->ctl, g->out_d, seq);
+                // the same smem-staged kernel as the health probe, with a peer-mapped source: the bulk
+                // copies cross NVLink, verification happens on the receiving GPU
+                hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>
+                    <<<(int)g->sms * kTmaCtasPerSm, (kTmaCW + 1) * 32, kTmaSmem, g->stream>>>(
+                        src, g->buf[g->cur ^ 1], n_vec, seed, 0u, g->ctl, g->out_d, seq);
                 cudaError_t e = cudaGetLastError();
                 cudaEventRecord(g->e1, g->stream);
                 if (e == cudaSuccess) e = cudaEventSynchronize(g->e1);
@@ -653,9 +655,15 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
         });
     };
 
-    // N-1 rounds of disjoint matchings (circle method); both directions of a pair run together
+    // N-1 rounds of disjoint matchings (circle method).  Default: one direction of every pair per
+    // half-round (a pull's read requests travel against the other direction's data, so running
+    // both directions at once measures ~635 GB/s per direction instead of the link's ~745 --
+    // profiles/r01_p2p_sweep_2gpu.csv); B2DP_P2P_BIDIR runs both directions together (full-duplex stress).
+    const bool bidir = opts && (opts->flags & B2DP_P2P_BIDIR);
     const int m = n % 2 ? n + 1 : n;
-    for (int r = 0; r < m - 1 && n > 1; ++r) {
+    for (int hr = 0; hr < 2 * (m - 1) && n > 1; ++hr) {
+        const int r = hr / 2, half = hr % 2;
+        if (bidir && half) continue;
         std::vector<std::pair<int, int>> pairs;
         auto add = [&](int a, int b) { if (a < n && b < n) pairs.push_back({a, b}); };  // >= n: bye
         add(m - 1, r);
@@ -665,6 +673,7 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
         std::vector<std::pair<int, int>> dirs;
         for (auto& p : pairs)
             for (int d = 0; d < 2; ++d) {
+                if (!bidir && d != half) continue;
                 const int i = d ? p.second : p.first, j = d ? p.first : p.second;
                 if (!can[(size_t)i * n + j]) continue;
                 prs.push_back(std::make_unique<PairRes>());

@@ -77,6 +77,7 @@ struct LabelSource {  // what the generators read; filled by the backend
     std::vector<int64_t> vram_bytes, sm_count;
     std::string driver_version, driver_src_version;
     bool part_supported[2] = {false, false};
+    std::vector<std::string> p2p_class;  // per device: "nvlink" | "pcie" | "none" (extension label p2p-link)
 };
 void create_labels(const std::string& kind, const std::map<std::string, int>& entries,
                    std::map<std::string, std::string>& out);

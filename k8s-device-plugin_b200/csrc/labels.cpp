@@ -38,9 +38,16 @@ void create_labels(const std::string& kind, const std::map<std::string, int>& en
     }
 }
 
+// Extension generator (no reference counterpart, BASELINE.json "labeller's link labels"): the
+// interconnect class of each GPU from the measured P2P matrix; same label scheme, and cleaned up
+// together with the reference's twelve.
+static const char kP2pLink[] = "p2p-link";
+
 void remove_old_node_labels(std::map<std::string, std::string>& labels) {  // main.go:55-74
-    for (const char* g : kGeneratorNames) labels.erase(label_prefix(g, false));
-    for (const char* g : kGeneratorNames) {
+    std::vector<std::string> names(kGeneratorNames, kGeneratorNames + 12);
+    names.push_back(kP2pLink);
+    for (const auto& g : names) labels.erase(label_prefix(g, false));
+    for (const auto& g : names) {
         const std::string k = label_prefix(g, true);
         auto it = labels.find(k);
         if (it != labels.end()) {
@@ -198,6 +205,11 @@ int generate_labels(const std::vector<Device>& devs, const LabelSource& src, con
             const bool v = src.native ? src.part_supported[which] : kfd_partition_supported(root, which);
             out[label_prefix(name, false)] = v ? "true" : "false";
         }
+    }
+    if (enabled(csv, kP2pLink) && src.native && !src.p2p_class.empty()) {
+        std::map<std::string, int> counts;
+        for (const auto& c : src.p2p_class) counts[c]++;
+        create_labels(kP2pLink, counts, out);
     }
     return B2DP_OK;
 }

@@ -192,6 +192,14 @@ def test_p2p_matrix(P):
                     assert lt[i, j] == oprobe.classify_link(True, float(gbs[i, j])) == 11, (i, j, gbs[i, j])
         # probing afterwards still verifies clean (the matrix only wrote spare buffers)
         assert all(r.healthy for r in ctx.probe_health())
+        # both directions at once (full-duplex stress) verifies too
+        gb2, lt2, mm2 = ctx.p2p_matrix(bidir=True)
+        assert (mm2 == 0).all() and (lt2 == lt).all()
+        # extension label (no reference counterpart): interconnect class per GPU
+        cls = "nvlink" if n > 1 else "none"
+        assert ctx.generate_labels(["p2p-link"]) == {
+            "amd.com/gpu.p2p-link": cls, "beta.amd.com/gpu.p2p-link": cls, "beta.amd.com/gpu.p2p-link." + cls: str(n)}
+        assert P.labeller.removeOldNodeLabels(ctx.generate_labels(["p2p-link", "vram"])) == {}
 
 
 def test_multi_gpu_fanout_concurrent(P):

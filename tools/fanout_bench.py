@@ -74,6 +74,13 @@ def main():
         out["p2p_mismatches"] = int(mm.sum())
         off = [float(gbs[i, j]) for i in range(n) for j in range(n) if i != j]
         out["p2p_gbs_min"], out["p2p_gbs_median"] = round(min(off), 1), round(statistics.median(off), 1)
+        out["p2p_frac_of_770_median"] = round(statistics.median(off) / 770.0, 4)
+        t0 = time.perf_counter()
+        gb2, lt2, mm2 = ctx.p2p_matrix(bidir=True)
+        out["p2p_bidir_matrix_s"] = round(time.perf_counter() - t0, 3)
+        off2 = [float(gb2[i, j]) for i in range(n) for j in range(n) if i != j]
+        out["p2p_bidir_gbs_min"], out["p2p_bidir_gbs_median"] = round(min(off2), 1), round(statistics.median(off2), 1)
+        out["p2p_bidir_mismatches"] = int(mm2.sum())
         assert ctx.start() == 0
         ids = sorted(devs)
         lat = []
