@@ -72,4 +72,19 @@ def test_device_plugin_main_registers_and_beats(pkg, kfd, tmp_path, short_dir):
         second = next(stream)                                           # arrives with the -pulse ticker
         assert [d.ID for d in second.devices] == [d.ID for d in first.devices]
         stream.cancel()
-    kubelet.server.stop(0)
+    # kubelet restart: kubelet.sock is re-created => the plugin serves again and re-registers
+    # (dpm/manager.go:73-84)
+    kubelet.server.stop(0).wait()
+    sock = os.path.join(plug_dir, "kubelet.sock")
+    if os.path.exists(sock):
+        os.unlink(sock)
+    time.sleep(0.3)
+    kubelet2 = FakeKubelet(sock, V)
+    regs = sorted((kubelet2.requests.get(timeout=15) for _ in range(2)), key=lambda r: r.resource_name)
+    assert [r.resource_name for r in regs] == ["amd.com/cpx_nps1", "amd.com/spx_nps1"]
+    with grpc.insecure_channel("unix://" + os.path.join(plug_dir, "amd.com_spx_nps1")) as ch:
+        stream = ch.unary_stream(V.LIST_AND_WATCH, request_serializer=lambda m: m.SerializeToString(),
+                                 response_deserializer=V.ListAndWatchResponse.FromString)(V.Empty())
+        assert len(next(stream).devices) == 16
+        stream.cancel()
+    kubelet2.server.stop(0)
