@@ -181,18 +181,14 @@ static inline void add_device(const BestEffortPolicy* p, DeviceSet& s, int node)
     s.ids.push_back(node);
 }
 
-// device.go:353-442.  `available`/`required` are device indices.  Returns error code or OK.
-static int candidate_subsets(const BestEffortPolicy* p, std::vector<int> available, const std::vector<int>& required,
-                             int size, std::vector<DeviceSet>& finals) {
-    finals.clear();
-    if (size <= 0) return B2DP_E_ALLOC_SUBSET_SIZE;
-    if ((int)available.size() < size) return B2DP_E_ALLOC_SUBSET_AVAIL;
+// filterPartitions (device.go:310-351): one group per physical GPU holding the available,
+// non-required NodeIds in ascending order; groups sorted by (len, ParentId), ties by DevId.
+static std::vector<Partitions> build_groups(const BestEffortPolicy* p, const std::vector<int>& available,
+                                            const std::vector<int>& required) {
     const auto& devs = p->devices;
     std::unordered_set<int> avail_nodes, req_nodes;
     for (int i : available) avail_nodes.insert(devs[i].node_id);
     for (int i : required) req_nodes.insert(devs[i].node_id);
-
-    // filterPartitions (device.go:310-351); ties on (len, ParentId) broken by DevId
     std::vector<Partitions> groups;
     for (const auto& kv : p->partitions) {
         Partitions f;
@@ -208,6 +204,19 @@ static int candidate_subsets(const BestEffortPolicy* p, std::vector<int> availab
         if (a.parent_id != b.parent_id) return a.parent_id < b.parent_id;
         return a.dev_id < b.dev_id;
     });
+    return groups;
+}
+
+// device.go:353-442, literally: two-phase enumeration of ordered group sequences (phase 2 is a
+// FIFO over partial sets).  Exponential in the number of groups; kept as the reference-shaped
+// implementation (used by b2dp_allocator_candidates and as the fallback of the fast path).
+static int candidate_subsets(const BestEffortPolicy* p, std::vector<int> available, const std::vector<int>& required,
+                             int size, std::vector<DeviceSet>& finals) {
+    finals.clear();
+    if (size <= 0) return B2DP_E_ALLOC_SUBSET_SIZE;
+    if ((int)available.size() < size) return B2DP_E_ALLOC_SUBSET_AVAIL;
+    const auto& devs = p->devices;
+    std::vector<Partitions> groups = build_groups(p, available, required);
 
     const int new_size = size - (int)required.size();
     const int n_groups = (int)groups.size();
@@ -252,6 +261,107 @@ static int candidate_subsets(const BestEffortPolicy* p, std::vector<int> availab
     return B2DP_OK;
 }
 
+// ---- exact fast path -----------------------------------------------------------------------
+// The reference enumerates ORDERED sequences of groups: every group but the last is taken whole,
+// the last contributes its lowest NodeIds until the size is reached; finals appear level by level
+// (number of groups used) and, within a level, in lexicographic order of the sequence; the first
+// strictly smallest total weight wins.  The weight of a set does not depend on the order its members
+// were added, so all orderings of the same (whole groups S, last group l) tie and the earliest of
+// them is sorted(S) followed by l.  The winner is therefore
+//      argmin over valid (S, l) of (weight, |S|+1, sorted(S)+[l])           -- 2^G * G states
+// instead of P(G, k) sequences (8 GPUs, size 7: 1,024 states instead of 40,320 sequences), with a
+// subset DP for the weights.  Same answer as the FIFO enumeration, bit for bit, including ties.
+constexpr int kFastMaxGroups = 16;
+
+static bool best_candidate_fast(const BestEffortPolicy* p, const std::vector<Partitions>& groups,
+                                const std::vector<int>& req_nodes, int new_size, DeviceSet& best_set, bool& found,
+                                double& n_sequences) {
+    const int G = (int)groups.size();
+    found = false;
+    n_sequences = 0;
+    if (G > kFastMaxGroups || new_size < 1) return false;  // not applicable: caller falls back
+    if (G == 0) return true;
+    // per-group prefix tables
+    std::vector<std::vector<int>> intra(G), reqp(G);            // [g][c]: first c ids of g among themselves / vs required
+    std::vector<std::vector<std::vector<int>>> crossp(G, std::vector<std::vector<int>>(G));  // [l][h][c]: prefix c of l vs all of h
+    int req_intra = 0;
+    for (size_t a = 0; a < req_nodes.size(); ++a)
+        for (size_t b = 0; b < a; ++b) req_intra += p->weight(req_nodes[b], req_nodes[a]);
+    for (int g = 0; g < G; ++g) {
+        const auto& ids = groups[g].ids;
+        intra[g].assign(ids.size() + 1, 0);
+        reqp[g].assign(ids.size() + 1, 0);
+        for (size_t c = 0; c < ids.size(); ++c) {
+            int add = 0, radd = 0;
+            for (size_t j = 0; j < c; ++j) add += p->weight(ids[j], ids[c]);
+            for (int r : req_nodes) radd += p->weight(ids[c], r);
+            intra[g][c + 1] = intra[g][c] + add;
+            reqp[g][c + 1] = reqp[g][c] + radd;
+        }
+        for (int h = 0; h < G; ++h) {
+            if (h == g) continue;
+            crossp[g][h].assign(ids.size() + 1, 0);
+            for (size_t c = 0; c < ids.size(); ++c) {
+                int add = 0;
+                for (int y : groups[h].ids) add += p->weight(ids[c], y);
+                crossp[g][h][c + 1] = crossp[g][h][c] + add;
+            }
+        }
+    }
+    auto full = [&](int g) { return (int)groups[g].ids.size(); };
+    // subset DP over whole groups: total size and weight (incl. pairs with the required devices)
+    const uint32_t n_sub = 1u << G;
+    std::vector<int> ssize(n_sub, 0), sweight(n_sub, 0);
+    for (uint32_t S = 1; S < n_sub; ++S) {
+        const int g = __builtin_ctz(S);
+        const uint32_t R = S & (S - 1);
+        int w = sweight[R] + intra[g][full(g)] + reqp[g][full(g)];
+        for (uint32_t T = R; T; T &= T - 1) { const int h = __builtin_ctz(T); w += crossp[g][h][full(g)]; }
+        sweight[S] = w;
+        ssize[S] = ssize[R] + full(g);
+    }
+    std::vector<double> fact(G + 1, 1.0);
+    for (int i = 1; i <= G; ++i) fact[i] = fact[i - 1] * i;
+    // (S, l) precedes (S2, l2) in the reference's order of equal-weight finals?
+    auto seq_less = [&](uint32_t S, int l, uint32_t S2, int l2) {
+        const int k = __builtin_popcount(S), k2 = __builtin_popcount(S2);
+        if (k != k2) return k < k2;
+        uint32_t a = S, b = S2;
+        while (a && b) {
+            const int x = __builtin_ctz(a), y = __builtin_ctz(b);
+            if (x != y) return x < y;
+            a &= a - 1; b &= b - 1;
+        }
+        return l < l2;
+    };
+    int best_w = INT32_MAX, best_l = -1;
+    uint32_t best_S = 0;
+    for (uint32_t S = 0; S < n_sub; ++S) {
+        if (ssize[S] >= new_size) continue;  // every whole-group prefix must still be short
+        const int need = new_size - ssize[S];
+        const int k = __builtin_popcount(S);
+        for (int l = 0; l < G; ++l) {
+            if (S & (1u << l)) continue;
+            if (full(l) < need) continue;
+            int w = sweight[S] + intra[l][need] + reqp[l][need] + req_intra;
+            for (uint32_t T = S; T; T &= T - 1) w += crossp[l][__builtin_ctz(T)][need];
+            n_sequences += fact[k];
+            if (w < best_w || (w == best_w && found && seq_less(S, l, best_S, best_l))) {
+                best_w = w; best_S = S; best_l = l; found = true;
+            }
+        }
+    }
+    if (!found) return true;
+    best_set.ids.clear();
+    best_set.weight = best_w;
+    for (uint32_t T = best_S; T; T &= T - 1)
+        for (int id : groups[__builtin_ctz(T)].ids) best_set.ids.push_back(id);
+    const int need = new_size - ssize[best_S];
+    for (int c = 0; c < need; ++c) best_set.ids.push_back(groups[best_l].ids[c]);
+    for (int r : req_nodes) best_set.ids.push_back(r);
+    return true;
+}
+
 int policy_allocate(BestEffortPolicy* p, const std::vector<std::string>& avail, const std::vector<std::string>& req,
                     int size, std::vector<std::string>& out, int* n_candidates, int* best_weight,
                     bool candidates_only) {
@@ -285,6 +395,25 @@ int policy_allocate(BestEffortPolicy* p, const std::vector<std::string>& avail, 
     // only matters for duplicate NodeIds)
     std::stable_sort(a_idx.begin(), a_idx.end(),
                      [&](int x, int y) { return p->devices[x].node_id < p->devices[y].node_id; });
+    if (!candidates_only) {
+        // exact fast path (see best_candidate_fast); identical result to the enumeration below
+        if (size <= 0) return B2DP_E_ALLOC_SUBSET_SIZE;
+        if ((int)a_idx.size() < size) return B2DP_E_ALLOC_SUBSET_AVAIL;
+        std::vector<int> req_nodes;
+        for (int r : r_idx) req_nodes.push_back(p->devices[r].node_id);
+        DeviceSet bs;
+        bool found = false;
+        double nseq = 0;
+        if (best_candidate_fast(p, build_groups(p, a_idx, r_idx), req_nodes, size - (int)r_idx.size(), bs, found, nseq)) {
+            if (n_candidates) *n_candidates = nseq > 2147483647.0 ? INT32_MAX : (int)nseq;
+            if (best_weight) *best_weight = found ? bs.weight : 0;
+            if (!found) return B2DP_E_PANIC;  // nil candidate deref, besteffort_policy.go:141
+            for (int id : bs.ids)             // besteffort_policy.go:141-148
+                for (int ai : a_idx)
+                    if (p->devices[ai].node_id == id) { out.push_back(p->devices[ai].id); break; }
+            return B2DP_OK;
+        }
+    }
     std::vector<DeviceSet> finals;
     int rc = candidate_subsets(p, a_idx, r_idx, size, finals);
     if (rc != B2DP_OK) return rc;
