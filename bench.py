@@ -351,10 +351,15 @@ def main():
                      "kernel_ms_mean": round(kernel_ms_mean, 5), "kernel_ms_mean_slowest_rank": round(kernel_ms_max_rank, 5)},
         "clocks": clocks,
     }
+    # the reference's own sysfs/kfd CPU path on this box's host cores, in the same run, at every N
+    # (C port of the Go walk on a synthetic N-device kfd tree in /dev/shm; single thread like the
+    # reference's single goroutine): ~0.2 s of CPU work
+    start_ms, beat_ms = kfd_walk_baseline(n)
+    line["reference_cpu_path"] = {"kfd_walk_stream_start_ms": round(start_ms, 4), "kfd_walk_heartbeat_ms": round(beat_ms, 4),
+                                  "n_devices": n, "threads": 1, "host_cores": os.cpu_count(), "kind": "port"}
     if n == 1:
         threads = os.cpu_count() or 1
         cpu_gbs, passes, dt = cpu_probe_baseline(threads)
-        start_ms, beat_ms = kfd_walk_baseline(1)
         line["cpu_baseline"] = {"value": round(cpu_gbs, 2), "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "256 MiB of the 1 GiB probe buffer, %d passes in %.1f s, host DRAM" % (passes, dt),
                                 "kfd_walk_stream_start_ms": round(start_ms, 4), "kfd_walk_heartbeat_ms": round(beat_ms, 4)}

@@ -127,7 +127,10 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     sys/class/kfd/kfd/topology, sys/devices/platform/amdgpu_xcp_*; no GPU work.
  *   "cuda:[k=v,...]"  real B200s.  keys: devices=0+1+2 (default all), bytes=<S per buffer,
  *                     default 1073741824>, min_gbs=<health threshold, default 3000>,
- *                     sysroot=<dir for numa_node lookups, default "/">, p2p_bytes=<default 268435456>.
+ *                     sysroot=<dir for numa_node lookups, default "/">, p2p_bytes=<default 268435456>,
+ *                     busy=probe|skip|shrink (what to do on a GPU another process is using; default probe),
+ *                     shrink_bytes=<prefix verified by busy=shrink, default 67108864>, ecc=1 (also fail on new
+ *                     uncorrected ECC errors, one NVML query per device per pass).
  * B2DP_E_NODRIVER (kfd: driver dir absent) | B2DP_E_NOGPU | B2DP_E_CUDA | B2DP_E_INVAL. */
 B2DP_API int b2dp_open(const char *backend_uri, b2dp_ctx **out);
 B2DP_API void b2dp_close(b2dp_ctx *ctx);
@@ -180,8 +183,11 @@ typedef struct b2dp_probe_result {
     float ms_event;             /* CUDA-event time of the probe kernel */
     float ms_device;            /* %globaltimer span inside the kernel */
     float gbs;                  /* bytes / ms_event */
-    float reserved;
+    uint32_t flags;             /* B2DP_RES_* */
 } b2dp_probe_result;
+#define B2DP_RES_SKIPPED_BUSY 0x1u /* busy=skip: another process owns the GPU, no pass ran, the last verdict stands */
+#define B2DP_RES_SHRUNK 0x2u       /* busy=shrink: a prefix (shrink_bytes) was verified without re-keying; no GB/s floor */
+#define B2DP_RES_ECC 0x4u          /* ecc=1: NVML reports new uncorrected ECC errors since open => Unhealthy */
 
 /* Launch the probe on every GPU of the context concurrently (one worker thread + stream per
  * GPU; all launched before any is waited on) and collect one result per device. */

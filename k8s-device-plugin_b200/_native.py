@@ -34,6 +34,7 @@ E_ALLOC_SUBSET_SIZE, E_ALLOC_SUBSET_AVAIL = -28, -29
 
 PROBE_VARIANT_TMA, PROBE_VARIANT_R128 = 0, 1
 PROBE_VIA_WORKERS = 0x10
+RES_SKIPPED_BUSY, RES_SHRUNK, RES_ECC = 1, 2, 4
 LW_INITIAL, LW_HEARTBEAT, LW_EXTERNAL_SOURCE, LW_NO_PROBE = 1, 2, 4, 8
 
 Id64 = C.c_char * 64
@@ -77,7 +78,7 @@ class ProbeResult(C.Structure):
     _fields_ = [("device", C.c_int32), ("healthy", C.c_int32), ("err", C.c_int32), ("seed", C.c_uint32),
                 ("checksum", C.c_uint64), ("expected_checksum", C.c_uint64), ("mismatches", C.c_uint64),
                 ("first_bad_word", C.c_uint64), ("bytes", C.c_uint64), ("ms_event", C.c_float),
-                ("ms_device", C.c_float), ("gbs", C.c_float), ("reserved", C.c_float)]
+                ("ms_device", C.c_float), ("gbs", C.c_float), ("flags", C.c_uint32)]
 
 
 class CycleOpts(C.Structure):

@@ -20,6 +20,7 @@ class ProbeResult:
     ms_event: float
     ms_device: float
     gbs: float
+    flags: int = 0
 
 
 @dataclass
@@ -112,7 +113,7 @@ class Context:
                                  lambda a, cap, pn: N.lib.b2dp_probe_health(self._h, C.byref(opts), a, cap, pn))
         N.check(rc, self._h)
         return [ProbeResult(r.device, bool(r.healthy), r.err, r.seed, r.checksum, r.expected_checksum, r.mismatches,
-                            r.first_bad_word, r.bytes, r.ms_event, r.ms_device, r.gbs) for r in arr[:n]]
+                            r.first_bad_word, r.bytes, r.ms_event, r.ms_device, r.gbs, r.flags) for r in arr[:n]]
 
     def probe_inject_fault(self, device: int, word_index: int, mask: int):
         N.check(N.lib.b2dp_probe_inject_fault(self._h, device, word_index, mask), self._h)

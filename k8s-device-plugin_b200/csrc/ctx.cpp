@@ -133,6 +133,13 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else if (p.first == "p2p_bytes") cfg.p2p_bytes = strtoull(p.second.c_str(), nullptr, 0);
             else if (p.first == "min_gbs") cfg.min_gbs = (float)atof(p.second.c_str());
             else if (p.first == "sysroot") cfg.sysroot = p.second;
+            else if (p.first == "busy") {
+                if (p.second == "probe") cfg.busy_policy = 0;
+                else if (p.second == "skip") cfg.busy_policy = 1;
+                else if (p.second == "shrink") cfg.busy_policy = 2;
+                else return fail(B2DP_E_INVAL, "busy= wants probe|skip|shrink");
+            } else if (p.first == "shrink_bytes") cfg.shrink_bytes = strtoull(p.second.c_str(), nullptr, 0);
+            else if (p.first == "ecc") cfg.check_ecc = p.second != "0";
             else return fail(B2DP_E_INVAL, "unknown cuda: option " + p.first);
         }
         if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");

@@ -67,6 +67,8 @@ struct Nvml {
     int (*minor_number)(void*, unsigned*) = nullptr;
     int (*vbios)(void*, char*, unsigned) = nullptr;
     int (*mig_mode)(void*, unsigned*, unsigned*) = nullptr;
+    int (*running_procs)(void*, unsigned*, void*) = nullptr;        // nvmlDeviceGetComputeRunningProcesses_v3
+    int (*ecc_total)(void*, int, int, unsigned long long*) = nullptr;  // nvmlDeviceGetTotalEccErrors
     bool ok = false;
     void load() {
         lib = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
@@ -77,6 +79,8 @@ struct Nvml {
         minor_number = (int (*)(void*, unsigned*))dlsym(lib, "nvmlDeviceGetMinorNumber");
         vbios = (int (*)(void*, char*, unsigned))dlsym(lib, "nvmlDeviceGetVbiosVersion");
         mig_mode = (int (*)(void*, unsigned*, unsigned*))dlsym(lib, "nvmlDeviceGetMigMode");
+        running_procs = (int (*)(void*, unsigned*, void*))dlsym(lib, "nvmlDeviceGetComputeRunningProcesses_v3");
+        ecc_total = (int (*)(void*, int, int, unsigned long long*))dlsym(lib, "nvmlDeviceGetTotalEccErrors");
         ok = init && init() == 0;
     }
 };
@@ -99,6 +103,10 @@ struct Gpu {
     std::string name, pci_device_id, vbios, family;
     int64_t vram = 0, sms = 0;
     bool mig_capable = false;
+    void* nvh = nullptr;                  // NVML device handle (optional)
+    unsigned long long ecc_base = 0;      // uncorrected volatile ECC count when the context was opened
+    bool have_ecc = false;
+    int last_healthy = 1;
     // worker
     std::thread th;
     std::mutex mu;
@@ -259,6 +267,9 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
             char busid[32];
             snprintf(busid, sizeof busid, "%08x:%02x:%02x.0", prop.pciDomainID, prop.pciBusID, prop.pciDeviceID);
             if (be->nvml.handle_by_bus_id(busid, &h) == 0) {
+                g->nvh = h;
+                if (be->nvml.ecc_total && be->nvml.ecc_total(h, 1 /*UNCORRECTED*/, 0 /*VOLATILE*/, &g->ecc_base) == 0)
+                    g->have_ecc = true;
                 unsigned mn = 0;
                 if (be->nvml.minor_number(h, &mn) == 0) { g->dev.card = (int)mn; have_minor = true; }
                 char vb[64] = {0};
@@ -395,6 +406,8 @@ struct ProbeJobResult {
     uint32_t seed = 0;
     unsigned long long seq = 0;
     bool seq_ok = false;
+    unsigned long long n_vec = 0;   // vectors this pass covers (shrunk on a busy GPU)
+    bool advance = true;            // false: verify-only prefix pass, buffers/seed stay as they are
 };
 
 static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uint32_t seed, uint32_t delta,
@@ -409,12 +422,14 @@ static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uin
 }
 
 // Enqueue one pass on g's stream (caller must have made g's device current).
-static void probe_issue(Gpu* g, ProbeJobResult* r, unsigned long long n_vec, uint32_t variant) {
+static void probe_issue(Gpu* g, ProbeJobResult* r, unsigned long long n_vec_full, uint32_t variant) {
     const uint32_t seed = g->seed, next = seed * 1664525u + 1013904223u;
+    const unsigned long long n_vec = r->n_vec ? r->n_vec : n_vec_full;
+    r->n_vec = n_vec;
     r->seed = seed;
     r->seq = ++g->seq;
     cudaEventRecord(g->e0, g->stream);
-    launch_probe(g, n_vec, variant, seed, seed ^ next, g->buf[g->cur], g->buf[g->cur ^ 1], r->seq);
+    launch_probe(g, n_vec, variant, seed, r->advance ? seed ^ next : 0u, g->buf[g->cur], g->buf[g->cur ^ 1], r->seq);
     r->ce = cudaGetLastError();
     cudaEventRecord(g->e1, g->stream);
 }
@@ -427,6 +442,13 @@ static void probe_collect(Gpu* g, ProbeJobResult* r, unsigned long long n_vec) {
     if (e != cudaSuccess) return;
     memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // published before the event fired
     r->seq_ok = r->out.seq == r->seq;
+    if (!r->advance) {
+        if (r->out.mismatches != 0 || !r->seq_ok) {  // repair the source buffer in place
+            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
+            cudaStreamSynchronize(g->stream);
+        }
+        return;
+    }
     g->seed = g->seed * 1664525u + 1013904223u;
     g->cur ^= 1;
     if (r->out.mismatches != 0 || !r->seq_ok) {
@@ -453,6 +475,25 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     std::vector<char> state(n, 0);  // 0 pending, 1 done, 2 timed out / busy
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
     for (size_t i = 0; i < n; ++i) res[i] = std::make_shared<ProbeJobResult>();
+    // busy policy (tenant workloads): a 2 GiB-traffic probe steals bandwidth from a pod that owns the
+    // GPU; `busy=skip` keeps the last verdict, `busy=shrink` verifies a small prefix without re-keying
+    std::vector<uint32_t> rflags(n, 0);
+    if (be->cfg.busy_policy != 0 && be->nvml.ok && be->nvml.running_procs) {
+        for (size_t i = 0; i < n; ++i) {
+            Gpu* g = be->gpus[i].get();
+            if (!g->nvh) continue;
+            unsigned cnt = 0;
+            const int nrc = be->nvml.running_procs(g->nvh, &cnt, nullptr);  // count only (INSUFFICIENT_SIZE = 7)
+            if ((nrc != 0 && nrc != 7) || cnt <= 1) continue;              // this process holds one context itself
+            if (be->cfg.busy_policy == 1) { state[i] = 3; rflags[i] = B2DP_RES_SKIPPED_BUSY; }
+            else {
+                unsigned long long sv = be->cfg.shrink_bytes / 16;
+                res[i]->n_vec = sv < n_vec ? (sv ? sv : 1) : n_vec;
+                res[i]->advance = false;
+                rflags[i] = B2DP_RES_SHRUNK;
+            }
+        }
+    }
 
     if (via_workers) {
         // fully isolated path: each GPU's own thread launches and waits; a wedged driver call can
@@ -460,6 +501,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         for (size_t i = 0; i < n; ++i) {  // launch everywhere before waiting anywhere
             Gpu* g = be->gpus[i].get();
             auto r = res[i];
+            if (state[i] != 0) continue;
             if (g->inflight.load()) { state[i] = 2; continue; }
             cs[i] = post(g, [g, r, n_vec, variant] {
                 probe_issue(g, r.get(), n_vec, variant);
@@ -475,6 +517,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         // the deadline is handed to its worker to be collected whenever it finishes.
         for (size_t i = 0; i < n; ++i) {
             Gpu* g = be->gpus[i].get();
+            if (state[i] != 0) continue;
             if (g->inflight.load()) { state[i] = 2; continue; }
             cudaSetDevice(g->ordinal);
             probe_issue(g, res[i].get(), n_vec, variant);
@@ -516,10 +559,18 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.device = (int)i;
         o.bytes = 2ull * be->cfg.bytes;
         o.first_bad_word = ~0ull;
-        if (state[i] == 2) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; continue; }
+        o.flags = rflags[i];
+        if (state[i] == 2) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; be->gpus[i]->last_healthy = 0; continue; }
+        if (state[i] == 3) { o.bytes = 0; o.healthy = be->gpus[i]->last_healthy; continue; }  // skipped: last verdict stands
         const ProbeJobResult& r = *res[i];
         o.seed = r.seed;
-        o.expected_checksum = expected_checksum(bc, n_words, r.seed);
+        if (r.n_vec == n_vec) o.expected_checksum = expected_checksum(bc, n_words, r.seed);
+        else {
+            std::array<unsigned long long, 32> bcs;
+            if (get_bitcounts(be, r.n_vec * 4, bcs, err) != B2DP_OK) { o.err = B2DP_E_CUDA; o.healthy = 0; continue; }
+            o.expected_checksum = expected_checksum(bcs, r.n_vec * 4, r.seed);
+            o.bytes = 2ull * r.n_vec * 16;
+        }
         if (r.ce != cudaSuccess) {
             o.err = B2DP_E_CUDA; o.healthy = 0;
             err = cuda_err("probe", r.ce) + " on " + be->gpus[i]->dev.id;
@@ -532,7 +583,17 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.ms_device = (float)((double)(r.out.t_end_ns - r.out.t_start_ns) * 1e-6);
         o.gbs = r.ms > 0 ? (float)((double)o.bytes / (double)r.ms * 1e-6) : 0.f;
         // verdict (oracle/probe.py probe_healthy)
-        o.healthy = (r.seq_ok && o.mismatches == 0 && o.checksum == o.expected_checksum && o.gbs >= min_gbs) ? 1 : 0;
+        // a shrunk pass shares the GPU with a tenant: integrity only, no bandwidth floor
+        const bool fast_enough = (o.flags & B2DP_RES_SHRUNK) ? true : o.gbs >= min_gbs;
+        o.healthy = (r.seq_ok && o.mismatches == 0 && o.checksum == o.expected_checksum && fast_enough) ? 1 : 0;
+        if (be->cfg.check_ecc && be->gpus[i]->have_ecc) {  // opt-in: an NVML query per device per pass
+            unsigned long long now = 0;
+            if (be->nvml.ecc_total(be->gpus[i]->nvh, 1, 0, &now) == 0 && now > be->gpus[i]->ecc_base) {
+                o.flags |= B2DP_RES_ECC;
+                o.healthy = 0;
+            }
+        }
+        be->gpus[i]->last_healthy = o.healthy;
     }
     return B2DP_OK;
 }

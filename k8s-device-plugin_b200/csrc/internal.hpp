@@ -94,6 +94,9 @@ struct CudaConfig {
     uint64_t p2p_bytes = 256ull << 20;
     float min_gbs = 3000.f;
     std::string sysroot = "/";
+    int busy_policy = 0;                 // 0 probe always, 1 skip busy GPUs, 2 shrink on busy GPUs
+    uint64_t shrink_bytes = 64ull << 20;
+    bool check_ecc = false;
 };
 int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err);
 void cuda_backend_close(CudaBackend*);

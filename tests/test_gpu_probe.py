@@ -215,3 +215,57 @@ def test_multi_gpu_fanout_concurrent(P):
         assert st.n_devices == n and st.n_unhealthy == 0
         slowest = max(r.ms_event for r in res)
         assert st.ms_probe < 3.0 * slowest + 1.0, (st.ms_probe, slowest)
+
+
+def test_busy_policy_skip_and_shrink(P):
+    """`busy=skip|shrink`: when another process owns the GPU the 2 GiB-traffic pass is skipped (last
+    verdict stands) or shrunk to a verify-only prefix that leaves the seed/ping-pong state alone."""
+    import subprocess
+    import sys
+    import time
+    helper = subprocess.Popen([sys.executable, "-c",
+                               "import torch,time; torch.zeros(1, device='cuda:0'); print('ready', flush=True); time.sleep(60)"],
+                              stdout=subprocess.PIPE, text=True)
+    try:
+        assert helper.stdout.readline().strip() == "ready"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            seen = len(pynvml.nvmlDeviceGetComputeRunningProcesses(pynvml.nvmlDeviceGetHandleByIndex(0)))
+        except Exception as e:       # noqa: BLE001
+            pytest.skip("NVML process accounting unavailable: %s" % e)
+        if seen < 1:
+            pytest.skip("NVML does not list foreign compute processes in this container")
+        nbytes, shrink = 32 * MiB, 1 * MiB
+        with _open(P, nbytes, ",busy=skip") as ctx:
+            (r,) = ctx.probe_health(min_gbs=1e-3)
+            assert r.flags & P._native.RES_SKIPPED_BUSY and r.healthy and r.bytes == 0 and r.err == 0
+            wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT, min_gbs=1e-3)
+            assert st.n_unhealthy == 0
+        with _open(P, nbytes, ",busy=shrink,shrink_bytes=%d" % shrink) as ctx:
+            seed = oprobe.initial_seed(0)
+            for _ in range(2):
+                (r,) = ctx.probe_health(min_gbs=1e9)                 # the GB/s floor does not apply to a shrunk pass
+                assert r.flags & P._native.RES_SHRUNK and r.healthy and r.bytes == 2 * shrink
+                assert r.seed == seed and r.mismatches == 0
+                assert r.checksum == r.expected_checksum == oprobe.expected_checksum(shrink // 4, seed)
+            ctx.probe_inject_fault(0, 100, 1)
+            (r,) = ctx.probe_health(min_gbs=1e-3)
+            assert not r.healthy and r.mismatches == 1 and r.first_bad_word == 100
+            (r,) = ctx.probe_health(min_gbs=1e-3)
+            assert r.healthy and r.seed == seed                       # repaired in place, state untouched
+            helper.kill()
+            helper.wait()
+            time.sleep(1.0)
+            (r,) = ctx.probe_health(min_gbs=1e-3)                     # alone again: a full pass
+            assert r.flags == 0 and r.bytes == 2 * nbytes and r.seed == seed and r.healthy
+            assert r.checksum == oprobe.expected_checksum(nbytes // 4, seed)
+    finally:
+        if helper.poll() is None:
+            helper.kill()
+
+
+def test_ecc_option_is_harmless(P):
+    with _open(P, 16 * MiB, ",ecc=1") as ctx:
+        (r,) = ctx.probe_health(min_gbs=1e-3)
+        assert r.healthy and not (r.flags & P._native.RES_ECC)
