@@ -11,7 +11,7 @@ times, single-threaded, median of K after 3 warm-ups:
   oracle_py : the Python oracle (for scale only)
 
 and reports algorithmic bytes (every node/link `properties` file read once) per tree.
-    python tools/kfd_parse_bench.py [--out profiles/rNN_kfd_parse_cpu.json]
+    python tests/bench_kfd_parse.py [--out profiles/rNN_kfd_parse_cpu.json]
 """
 import argparse
 import ctypes as C
