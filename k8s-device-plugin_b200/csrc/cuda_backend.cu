@@ -2,9 +2,11 @@
 //
 // One worker thread per GPU owns that GPU's primary context, stream, events, pinned result
 // block and the two probe buffers; callers (cgo threads, ctypes, gRPC handlers) never touch
-// a CUDA "current device".  A probe request is posted to every worker before any is waited
-// on, so the N kernels run concurrently; a worker that does not answer before the deadline
-// yields B2DP_E_TIMEOUT / Unhealthy for its device only.
+// a CUDA "current device".  The heartbeat probe enqueues one pass on every GPU's stream before
+// waiting on any (so the N kernels run concurrently), either from the calling thread with event
+// polling (default, lowest latency) or through the per-GPU workers (B2DP_PROBE_VIA_WORKERS); a
+// device that does not finish before the deadline yields B2DP_E_TIMEOUT / Unhealthy for that
+// device only and is collected later by its worker.
 //
 // Replaces: the node-level text check `simpleHealthCheck` (plugin.go:161-206), the exporter
 // round trip `getGPUHealth` (exporter/health.go:42-82) and the kfd link `type` read
@@ -514,7 +516,10 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     } else {
         // low-latency path (default): the calling thread enqueues on every GPU's stream, then polls
         // the completion events; no thread hand-offs on the critical path.  A device that misses
-        // the deadline is handed to its worker to be collected whenever it finishes.
+        // the deadline is handed to its worker to be collected whenever it finishes.  The caller's
+        // current CUDA device is restored before returning.
+        int prev_dev = -1;
+        cudaGetDevice(&prev_dev);
         for (size_t i = 0; i < n; ++i) {
             Gpu* g = be->gpus[i].get();
             if (state[i] != 0) continue;
@@ -551,6 +556,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
                 g->inflight.store(false);
             });
         }
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
     }
 
     out.assign(n, b2dp_probe_result{});
