@@ -54,6 +54,14 @@ def test_open_errors(P, tmp_path):
     with pytest.raises(P._native.B2dpError) as ei:
         P.Context("bogus:")
     assert ei.value.code == P._native.E_INVAL
+    with pytest.raises(P._native.B2dpError) as ei:
+        P.Context("cuda:busy=sometimes")
+    assert ei.value.code == P._native.E_INVAL
+    import torch
+    if not torch.cuda.is_available():            # no GPU: the cuda: backend fails loudly, no fallback
+        with pytest.raises(P._native.B2dpError) as ei:
+            P.Context("cuda:")
+        assert ei.value.code == P._native.E_NOGPU
 
 
 # ---- amdgpu_test.go through the ABI -----------------------------------------------------------
