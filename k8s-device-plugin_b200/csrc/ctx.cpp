@@ -32,7 +32,7 @@ struct b2dp_ctx {
     std::string sysroot;        // kfd: plays "/"; cuda: where numa_node is looked up
     CudaBackend* cuda = nullptr;
     std::mutex mu;              // guards policy / allocator_init_error / links
-    BestEffortPolicy* policy = nullptr;
+    std::shared_ptr<BestEffortPolicy> policy;  // shared: a restart must not free it under a running Allocate
     bool started = false, allocator_init_error = false;
     std::vector<Link> links;    // cuda: measured link list (node ids), filled by the p2p matrix
     bool have_links = false;
@@ -160,7 +160,6 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
 extern "C" void b2dp_close(b2dp_ctx* c) {
     if (!c) return;
     if (c->cuda) cuda_backend_close(c->cuda);
-    if (c->policy) policy_free(c->policy);
     delete c;
 }
 
@@ -342,6 +341,7 @@ extern "C" int b2dp_list_and_watch(b2dp_ctx* c, const char* resource, const b2dp
         bool have_source = false;
         if (flags & B2DP_LW_EXTERNAL_SOURCE) {
             have_source = true;
+            if (opts && opts->src_n > 0 && (!opts->src_ids || !opts->src_health)) return B2DP_E_INVAL;
             for (int j = 0; opts && j < opts->src_n; ++j) hmap[opts->src_ids[j]] = opts->src_health[j] ? 1 : 0;
         } else if (!(flags & B2DP_LW_NO_PROBE) && c->kind == b2dp_ctx::CUDA) {
             std::vector<b2dp_probe_result> res;
@@ -466,12 +466,11 @@ extern "C" int b2dp_start(b2dp_ctx* c) {
     int rc = enumerate_ctx(c, devs);  // plugin.go:85 getDevices()
     if (rc != B2DP_OK) return rc;
     std::lock_guard<std::mutex> g(c->mu);
-    if (c->policy) { policy_free(c->policy); c->policy = nullptr; }
-    c->policy = policy_new();
-    if (c->kind == b2dp_ctx::KFD) rc = policy_init_dir(c->policy, devs, go::join(c->sysroot, "sys/class/kfd/kfd/topology/nodes"));
+    c->policy = std::shared_ptr<BestEffortPolicy>(policy_new(), policy_free);
+    if (c->kind == b2dp_ctx::KFD) rc = policy_init_dir(c->policy.get(), devs, go::join(c->sysroot, "sys/class/kfd/kfd/topology/nodes"));
     else {
         rc = ensure_links(c, devs);
-        if (rc == B2DP_OK) rc = policy_init_links(c->policy, devs, c->links);
+        if (rc == B2DP_OK) rc = policy_init_links(c->policy.get(), devs, c->links);
     }
     c->started = true;
     c->allocator_init_error = rc != B2DP_OK;  // plugin.go:86-90
@@ -490,17 +489,17 @@ extern "C" int b2dp_preferred_allocation(b2dp_ctx* c, const char* const* availab
                                          const char* const* must_include, int nm, int size, char (*out)[64], int cap,
                                          int* n) {
     if (!c || !n || na < 0 || nm < 0 || (na && !available) || (nm && !must_include) || cap < 0) return B2DP_E_INVAL;
-    BestEffortPolicy* p;
+    std::shared_ptr<BestEffortPolicy> p;
     {
         std::lock_guard<std::mutex> g(c->mu);
-        if (!c->policy) c->policy = policy_new();  // Allocate before Start => "Init method must be called"
+        if (!c->policy) c->policy = std::shared_ptr<BestEffortPolicy>(policy_new(), policy_free);  // Allocate before Start => "Init method must be called"
         p = c->policy;
     }
     std::vector<std::string> a, r, ids;
     for (int i = 0; i < na; ++i) a.emplace_back(available[i] ? available[i] : "");
     for (int i = 0; i < nm; ++i) r.emplace_back(must_include[i] ? must_include[i] : "");
     *n = 0;
-    int rc = policy_allocate(p, a, r, size, ids, nullptr, nullptr, false);
+    int rc = policy_allocate(p.get(), a, r, size, ids, nullptr, nullptr, false);
     if (rc != B2DP_OK) return fail(rc, std::string("unable to get preferred allocation list. Error:") + b2dp_strerror(rc));
     *n = (int)ids.size();
     if (*n > cap) return B2DP_E_NOSPC;
