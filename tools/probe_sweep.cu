@@ -54,6 +54,67 @@ __global__ void plain_copy(const uint4* __restrict__ s, uint4* __restrict__ d, u
          i += (unsigned long long)gridDim.x * blockDim.x) d[i] = s[i];
 }
 
+// ---- ceilings: what pure reads and pure writes reach on this part (tool-only kernels) ---------
+template <int U>
+__global__ void read_only(const uint4* __restrict__ s, unsigned long long n, unsigned long long* sink) {
+    unsigned long long acc = 0;
+    const unsigned long long chunk = (unsigned long long)blockDim.x * U, n_full = n / chunk;
+    for (unsigned long long c = blockIdx.x; c < n_full; c += gridDim.x) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ldg_na(s + c * chunk + threadIdx.x + (unsigned long long)u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += (unsigned long long)v[u].x + v[u].y + v[u].z + v[u].w;
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;   // keep the loads alive
+}
+__global__ void write_only(uint4* __restrict__ d, unsigned long long n, uint32_t seed) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t m0 = (uint32_t)(i * 4ull) * kPatternMul;
+        stg_na(d + i, make_uint4(m0 ^ seed, (m0 + kPatternMul) ^ seed, (m0 + 2u * kPatternMul) ^ seed, (m0 + 3u * kPatternMul) ^ seed));
+    }
+}
+// bulk-copy read-only: the ring is filled and drained without any store
+template <int TILE_VEC, int STAGES>
+__global__ void __launch_bounds__(160) read_only_tma(const uint4* __restrict__ src, unsigned long long n_vec, unsigned long long* sink) {
+    constexpr uint32_t TILE_BYTES = TILE_VEC * 16u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4* tiles = reinterpret_cast<uint4*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE_BYTES);
+    uint64_t* done = full + STAGES;
+    const unsigned long long n_tiles = n_vec / TILE_VEC;
+    const unsigned long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+    unsigned long long acc = 0;
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            for (unsigned long long k = 0; k < my_tiles; ++k) {
+                const int slot = (int)(k % STAGES);
+                if (k >= STAGES) mbar_wait(&done[slot], (uint32_t)(((k / STAGES) - 1) & 1));
+                mbar_expect_tx(&full[slot], TILE_BYTES);
+                bulk_g2s(tiles + (size_t)slot * TILE_VEC, src + (blockIdx.x + k * gridDim.x) * TILE_VEC, TILE_BYTES, &full[slot]);
+            }
+        }
+    } else {
+        const int ct = threadIdx.x - 32;
+        for (unsigned long long k = 0; k < my_tiles; ++k) {
+            const int slot = (int)(k % STAGES);
+            mbar_wait(&full[slot], (uint32_t)((k / STAGES) & 1));
+            const uint4* tile = tiles + (size_t)slot * TILE_VEC;
+#pragma unroll
+            for (int u = 0; u < TILE_VEC / 128; ++u) { uint4 v = tile[ct + u * 128]; acc += (unsigned long long)v.x + v.y + v.z + v.w; }
+            mbar_arrive(&done[slot]);
+        }
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+
 struct Cfg { std::string name; LaunchFn fn; int ctas_per_sm; };
 
 int main(int argc, char** argv) {
@@ -120,6 +181,32 @@ int main(int argc, char** argv) {
                    2.0 * bytes / r2.first / 1e6, 2.0 * bytes / r2.second / 1e6);
         }
         // restore pattern in a (plain_copy/memcpy left b == a; a is intact)
+        unsigned long long* sink; CK(cudaMalloc(&sink, 8));
+        for (int k : {2, 4, 8}) {
+            auto rr = time_it([&] { read_only<4><<<sms * k, 512, 0, st>>>(B.a, B.n_vec, sink); });
+            printf("read_only_t512_u4,%d,%d,%.4f,%.4f,%.1f,%.1f,1\n", k, sms * k, rr.first, rr.second, 1.0 * bytes / rr.first / 1e6, 1.0 * bytes / rr.second / 1e6);
+            auto r8 = time_it([&] { read_only<8><<<sms * k, 256, 0, st>>>(B.a, B.n_vec, sink); });
+            printf("read_only_t256_u8,%d,%d,%.4f,%.4f,%.1f,%.1f,1\n", k, sms * k, r8.first, r8.second, 1.0 * bytes / r8.first / 1e6, 1.0 * bytes / r8.second / 1e6);
+        }
+        {
+            constexpr size_t sm3 = 3 * 1024 * 16 + 64, sm6 = 6 * 1024 * 16 + 128;
+            CK(cudaFuncSetAttribute(read_only_tma<1024, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+            CK(cudaFuncSetAttribute(read_only_tma<1024, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm6));
+            for (int k : {1, 2, 3}) {
+                auto rt = time_it([&] { read_only_tma<1024, 3><<<sms * k, 160, sm3, st>>>(B.a, B.n_vec, sink); });
+                printf("read_only_tma_tv1024_st3,%d,%d,%.4f,%.4f,%.1f,%.1f,1\n", k, sms * k, rt.first, rt.second, 1.0 * bytes / rt.first / 1e6, 1.0 * bytes / rt.second / 1e6);
+            }
+            for (int k : {1, 2}) {
+                auto rt = time_it([&] { read_only_tma<1024, 6><<<sms * k, 160, sm6, st>>>(B.a, B.n_vec, sink); });
+                printf("read_only_tma_tv1024_st6,%d,%d,%.4f,%.4f,%.1f,%.1f,1\n", k, sms * k, rt.first, rt.second, 1.0 * bytes / rt.first / 1e6, 1.0 * bytes / rt.second / 1e6);
+            }
+        }
+        for (int k : {2, 4, 8, 16}) {
+            auto rw = time_it([&] { write_only<<<sms * k, 512, 0, st>>>(B.b, B.n_vec, 7u); });
+            printf("write_only_t512,%d,%d,%.4f,%.4f,%.1f,%.1f,1\n", k, sms * k, rw.first, rw.second, 1.0 * bytes / rw.first / 1e6, 1.0 * bytes / rw.second / 1e6);
+        }
+        auto rm = time_it([&] { CK(cudaMemsetAsync(B.b, 0, bytes, st)); });
+        printf("memset,0,0,%.4f,%.4f,%.1f,%.1f,1\n", rm.first, rm.second, 1.0 * bytes / rm.first / 1e6, 1.0 * bytes / rm.second / 1e6);
     }
 
     unsigned long long seq = 0;
