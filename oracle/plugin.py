@@ -1,10 +1,9 @@
 """Oracle restatement of internal/pkg/plugin/plugin.go, internal/pkg/exporter/health.go
 and cmd/k8s-device-plugin/main.go:42-91 (test infrastructure only)."""
-import os
 
 from . import amdgpu, gosem
 from .allocator import Device
-from .gosem import ParseError
+
 
 Healthy = "Healthy"        # vendor/k8s.io/kubelet/pkg/apis/deviceplugin/v1beta1/constants.go:21
 Unhealthy = "Unhealthy"    # constants.go:23

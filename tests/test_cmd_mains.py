@@ -3,11 +3,9 @@ import importlib
 import io
 import json
 import os
-import queue
 import sys
 import threading
 import time
-from concurrent import futures
 
 import grpc
 

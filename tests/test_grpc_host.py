@@ -5,7 +5,6 @@ the plugin's unix socket.  CPU only."""
 import importlib
 import os
 import queue
-import threading
 from concurrent import futures
 
 import grpc

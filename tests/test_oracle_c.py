@@ -1,6 +1,5 @@
 """Cross-check the C restatements (oracle/kfd_walk.c, oracle/probe_oracle.c -- the timed CPU
 baseline of bench.py) against the Python oracle on every fixture.  CPU only."""
-import collections
 
 import numpy as np
 import pytest
