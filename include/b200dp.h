@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B2DP_ABI_VERSION 1
+#define B2DP_ABI_VERSION 2
 #if defined(__GNUC__)
 #define B2DP_API __attribute__((visibility("default")))
 #else
@@ -225,6 +225,9 @@ typedef struct b2dp_cycle_opts {
                                         list once per stream), enumerating only if there has been none */
 #define B2DP_LW_EXTERNAL_SOURCE 0x4u /* merge src_* instead of running the GPU probe */
 #define B2DP_LW_NO_PROBE 0x8u        /* heartbeat without a per-device source: default health only */
+#define B2DP_LW_LINK_CHECK 0x10u     /* heartbeat also re-measures the NVLink P2P matrix (64 MiB per directed pair,
+                                        both directions at once, ~10 ms on 8 GPUs): a device with a corrupting link or a
+                                        link that fell out of its measured class is reported Unhealthy */
 
 typedef struct b2dp_cycle_stats {
     int32_t n_devices;        /* devices in the response */
@@ -238,6 +241,8 @@ typedef struct b2dp_cycle_stats {
     float probe_gbs_min;      /* over devices, 0 if no probe ran */
     float probe_gbs_sum;
     uint64_t probe_bytes;     /* algorithmic bytes over all devices */
+    float ms_link_check;      /* B2DP_LW_LINK_CHECK: time of the P2P matrix */
+    int32_t n_link_faults;    /* directed pairs that failed the link check */
 } b2dp_cycle_stats;
 
 /* One ListAndWatch send.  Writes the serialized v1beta1.ListAndWatchResponse protobuf

@@ -35,7 +35,7 @@ E_ALLOC_SUBSET_SIZE, E_ALLOC_SUBSET_AVAIL = -28, -29
 PROBE_VARIANT_TMA, PROBE_VARIANT_R128 = 0, 1
 PROBE_VIA_WORKERS = 0x10
 RES_SKIPPED_BUSY, RES_SHRUNK, RES_ECC = 1, 2, 4
-LW_INITIAL, LW_HEARTBEAT, LW_EXTERNAL_SOURCE, LW_NO_PROBE = 1, 2, 4, 8
+LW_INITIAL, LW_HEARTBEAT, LW_EXTERNAL_SOURCE, LW_NO_PROBE, LW_LINK_CHECK = 1, 2, 4, 8, 16
 
 Id64 = C.c_char * 64
 
@@ -90,7 +90,8 @@ class CycleStats(C.Structure):
     _fields_ = [("n_devices", C.c_int32), ("n_unhealthy", C.c_int32), ("homogeneous", C.c_int32),
                 ("node_healthy", C.c_int32), ("ms_total", C.c_float), ("ms_enumerate", C.c_float),
                 ("ms_probe", C.c_float), ("ms_encode", C.c_float), ("probe_gbs_min", C.c_float),
-                ("probe_gbs_sum", C.c_float), ("probe_bytes", C.c_uint64)]
+                ("probe_gbs_sum", C.c_float), ("probe_bytes", C.c_uint64), ("ms_link_check", C.c_float),
+                ("n_link_faults", C.c_int32)]
 
 
 class P2pOpts(C.Structure):
@@ -153,10 +154,16 @@ SIGNATURES = {
     "b2dp_generate_labels": (_i, [_vp, _cp, _P(Label), _i, _ip]),
     "b2dp_remove_old_node_labels": (_i, [_P(Label), _i, _ip]),
 }
+ABI_VERSION = 2          # must equal B2DP_ABI_VERSION in include/b200dp.h (struct layouts above)
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)   # AttributeError here = the .so does not export what the header declares
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+if lib.b2dp_abi_version() != ABI_VERSION:
+    raise ImportError("libb200dp.so has ABI %d, this binding expects %d: rebuild (make -C k8s-device-plugin_b200/csrc)"
+                      % (lib.b2dp_abi_version(), ABI_VERSION))
 
 
 class B2dpError(Exception):

@@ -36,6 +36,8 @@ class CycleStats:
     probe_gbs_min: float
     probe_gbs_sum: float
     probe_bytes: int
+    ms_link_check: float = 0.0
+    n_link_faults: int = 0
 
 
 class Context:
@@ -157,7 +159,7 @@ class Context:
         del keep
         stats = CycleStats(st.n_devices, st.n_unhealthy, bool(st.homogeneous), bool(st.node_healthy), st.ms_total,
                            st.ms_enumerate, st.ms_probe, st.ms_encode, st.probe_gbs_min, st.probe_gbs_sum,
-                           st.probe_bytes)
+                           st.probe_bytes, st.ms_link_check, st.n_link_faults)
         return bytes(self._buf[:ln.value]), stats
 
     # ---- Allocate ------------------------------------------------------------------------

@@ -360,6 +360,32 @@ extern "C" int b2dp_list_and_watch(b2dp_ctx* c, const char* resource, const b2dp
                 if (r.gbs < st.probe_gbs_min) st.probe_gbs_min = r.gbs;
             }
             if (res.empty()) st.probe_gbs_min = 0;
+            if ((flags & B2DP_LW_LINK_CHECK) && devs.size() > 1) {
+                // optional: re-measure the NVLink matrix (both directions at once, one timed pass per
+                // pair) and fail a device whose link to any peer delivers corrupt data or has dropped
+                // out of the class it had when the topology was first measured
+                const int n = (int)devs.size();
+                std::vector<float> gbs((size_t)n * n);
+                std::vector<int32_t> lt((size_t)n * n);
+                std::vector<uint64_t> mm((size_t)n * n);
+                b2dp_p2p_opts po{};
+                po.bytes = 64ull << 20; po.iters = 1; po.flags = B2DP_P2P_BIDIR;
+                const double l0 = now_ms();
+                rc = cuda_p2p_matrix(c->cuda, &po, gbs.data(), lt.data(), mm.data(), n, err);
+                st.ms_link_check = (float)(now_ms() - l0);
+                if (rc != B2DP_OK) return fail(rc, err);
+                std::lock_guard<std::mutex> g(c->mu);
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < n; ++j) {
+                        if (i == j) continue;
+                        bool bad = mm[(size_t)i * n + j] != 0;
+                        if (c->have_links)
+                            for (const auto& l : c->links)
+                                if (l.from == devs[i].node_id && l.to == devs[j].node_id && l.type == 11 && lt[(size_t)i * n + j] != 11)
+                                    bad = true;
+                        if (bad) { hmap[devs[i].id] = 0; st.n_link_faults++; }
+                    }
+            }
         }
         for (size_t i = 0; i < sel.size(); ++i) {  // health.go:93-105
             if (!have_source) { healthy[i] = def; continue; }

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(P):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(P._native.SIGNATURES)
-    assert lib.b2dp_abi_version() == 1
+    assert lib.b2dp_abi_version() == int(re.search(r"#define B2DP_ABI_VERSION (\d+)", hdr).group(1)) == P._native.ABI_VERSION
 
 
 def test_no_cpu_fallback_for_the_probe(P, kfd, tmp_path):

@@ -215,6 +215,12 @@ def test_multi_gpu_fanout_concurrent(P):
         assert st.n_devices == n and st.n_unhealthy == 0
         slowest = max(r.ms_event for r in res)
         assert st.ms_probe < 3.0 * slowest + 1.0, (st.ms_probe, slowest)
+        # heartbeat + NVLink link check against the topology measured at Start()
+        ctx.start()
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT | P._native.LW_LINK_CHECK)
+        assert st.n_unhealthy == 0 and st.n_link_faults == 0
+        assert (st.ms_link_check > 0) == (n > 1)
+        assert all(r.healthy for r in ctx.probe_health())
 
 
 def test_busy_policy_skip_and_shrink(P):

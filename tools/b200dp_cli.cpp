@@ -30,6 +30,10 @@ static double median(std::vector<double> v) { std::sort(v.begin(), v.end()); ret
 
 int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s <backend-uri> <command> [args]\n", argv[0]); return 2; }
+    if (b2dp_abi_version() != B2DP_ABI_VERSION) {
+        fprintf(stderr, "libb200dp.so has ABI %d, this host was built against %d\n", b2dp_abi_version(), B2DP_ABI_VERSION);
+        return 3;
+    }
     b2dp_ctx* ctx = nullptr;
     int rc = b2dp_open(argv[1], &ctx);
     if (rc != B2DP_OK) return die(nullptr, "b2dp_open", rc);
