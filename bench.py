@@ -319,6 +319,36 @@ def main():
     msg = pkg.v1beta1.ListAndWatchResponse.FromString(wire)
     assert len(msg.devices) == 1 and msg.devices[0].health == "Healthy", msg
 
+    # ---- the kubelet's view: heartbeat tick -> ListAndWatchResponse received over the plugin's unix
+    # socket (grpcio server + client stream in this process); informative, not the timed `e2e` ------
+    grpc_ms = None
+    try:
+        import grpc
+        import statistics
+        srv_mod = importlib.import_module(PKG + ".server")
+        V = pkg.v1beta1
+        d = tempfile.mkdtemp(prefix="b2b_", dir="/tmp")
+        plugin = pkg.plugin.AMDGPUPlugin(ctx, "gpu")
+        plugin.Start = lambda: None
+        server = srv_mod.PluginServer(plugin, plugin_dir=d).start()
+        with grpc.insecure_channel("unix://" + server.socket_path) as ch:
+            stream = ch.unary_stream(V.LIST_AND_WATCH, request_serializer=lambda m: m.SerializeToString(),
+                                     response_deserializer=lambda b: b)(V.Empty())
+            next(stream)
+            lat = []
+            for i in range(105):
+                t0 = time.perf_counter()
+                plugin.Heartbeat.put(True)
+                next(stream)
+                if i >= 5:
+                    lat.append((time.perf_counter() - t0) * 1e3)
+            stream.cancel()
+        server.stop()
+        grpc_ms = max_over_ranks(statistics.median(lat))
+    except Exception as e:      # noqa: BLE001
+        print("grpc leg skipped: %r" % (e,), file=sys.stderr)
+        grpc_ms = max_over_ranks(-1.0)
+
     clocks = sampler.stop(windows) if sampler else None
     if rank != 0:
         ctx.close()
@@ -343,6 +373,7 @@ def main():
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 48 * 1 + len(wire),
                 "cycle_ms": round(t_e2e / args.steps * 1e3, 4), "ms_enumerate": round(enum_ms / args.steps, 5),
                 "ms_encode": round(enc_ms / args.steps, 5), "response_bytes": len(wire),
+                "heartbeat_to_kubelet_grpc_ms": None if grpc_ms is None or grpc_ms < 0 else round(grpc_ms, 4),
                 "note": "no bulk host buffers on this path: kernel arguments in, 48-byte result block (pinned mapped) + serialized response out"},
         "gpu_launches": args.steps * n,
         "unhealthy_verdicts": int(unhealthy),
