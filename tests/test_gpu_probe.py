@@ -275,3 +275,30 @@ def test_ecc_option_is_harmless(P):
     with _open(P, 16 * MiB, ",ecc=1") as ctx:
         (r,) = ctx.probe_health(min_gbs=1e-3)
         assert r.healthy and not (r.flags & P._native.RES_ECC)
+
+
+def test_word_index_wraps_past_16_gib(P):
+    """Maximum sizes: a buffer larger than 2^32 words (16 GiB) makes the 32-bit word index of the
+    pattern wrap.  Size-independent property: one full period of (uint32(i) * K) ^ seed visits every
+    32-bit value once, so its sum is 2^31 * (2^32 - 1) for any seed; the remainder is a plain prefix."""
+    import torch
+    free, total = torch.cuda.mem_get_info(0)
+    extra_words = 16 * MiB // 4
+    n_words = (1 << 32) + extra_words
+    nbytes = n_words * 4
+    if free < 2 * nbytes + (4 << 30):
+        pytest.skip("not enough free HBM for two %.1f GiB buffers" % (nbytes / 2 ** 30))
+    period_sum = (1 << 31) * ((1 << 32) - 1)
+    with _open(P, nbytes) as ctx:
+        seed = oprobe.initial_seed(0)
+        for _ in range(2):
+            (r,) = ctx.probe_health()
+            want = (period_sum + oprobe.expected_checksum(extra_words, seed)) & oprobe.NO_BAD
+            assert r.mismatches == 0 and r.checksum == r.expected_checksum == want and r.healthy
+            assert r.bytes == 2 * nbytes
+            seed = oprobe.next_seed(seed)
+        # the words just past the wrap repeat the start of the pattern
+        assert np.array_equal(ctx.probe_peek(0, 1 << 32, 4096), oprobe.pattern(4096, seed))
+        ctx.probe_inject_fault(0, (1 << 32) + 5, 0x80)
+        (r,) = ctx.probe_health()
+        assert (r.mismatches, r.first_bad_word, r.healthy) == (1, (1 << 32) + 5, False)
