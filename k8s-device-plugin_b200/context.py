@@ -1,5 +1,6 @@
 """Context: one opened backend of libb200dp (`kfd:<sysroot>` parity mode or `cuda:` real B200s)."""
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -48,6 +49,7 @@ class Context:
         if rc != N.OK:
             raise N.B2dpError(rc, N.lib.b2dp_last_error(None).decode())
         self._buf = (C.c_uint8 * (1 << 16))()
+        self._buf_lock = threading.Lock()      # one response buffer, several gRPC handler threads
 
     def close(self):
         if self._h:
@@ -149,18 +151,20 @@ class Context:
             keep = (ids, hl)
         ln = C.c_size_t(0)
         st = N.CycleStats()
-        rc = N.lib.b2dp_list_and_watch(self._h, resource.encode(), C.byref(opts), self._buf, len(self._buf),
-                                       C.byref(ln), C.byref(st))
-        if rc == N.E_NOSPC:
-            self._buf = (C.c_uint8 * (ln.value * 2))()
+        with self._buf_lock:
             rc = N.lib.b2dp_list_and_watch(self._h, resource.encode(), C.byref(opts), self._buf, len(self._buf),
                                            C.byref(ln), C.byref(st))
-        N.check(rc, self._h)
+            if rc == N.E_NOSPC:
+                self._buf = (C.c_uint8 * (ln.value * 2))()
+                rc = N.lib.b2dp_list_and_watch(self._h, resource.encode(), C.byref(opts), self._buf, len(self._buf),
+                                               C.byref(ln), C.byref(st))
+            N.check(rc, self._h)
+            wire = bytes(self._buf[:ln.value])
         del keep
         stats = CycleStats(st.n_devices, st.n_unhealthy, bool(st.homogeneous), bool(st.node_healthy), st.ms_total,
                            st.ms_enumerate, st.ms_probe, st.ms_encode, st.probe_gbs_min, st.probe_gbs_sum,
                            st.probe_bytes, st.ms_link_check, st.n_link_faults)
-        return bytes(self._buf[:ln.value]), stats
+        return wire, stats
 
     # ---- Allocate ------------------------------------------------------------------------
     def device_specs(self, ids: List[str]):
