@@ -57,3 +57,15 @@ def Reconcile(node_labels: Optional[Dict[str, str]], labels: Dict[str, str]) -> 
     removeOldNodeLabels(node_labels)
     node_labels.update(labels)
     return node_labels
+
+
+def node_label_merge_patch(before: Optional[Dict[str, str]], after: Dict[str, str]) -> str:
+    """The JSON merge patch (RFC 7386, `kubectl patch node --type merge`) that takes a node's label
+    map from `before` to `after`: changed/new labels carry their value, removed ones null.  This is
+    the wire body a K8s client sends for the reference's `client.Update` (controller.go:47-55)
+    when only labels change."""
+    import json
+    before = before or {}
+    labels = {k: v for k, v in after.items() if before.get(k) != v}
+    labels.update({k: None for k in before if k not in after})
+    return json.dumps({"metadata": {"labels": labels}}, sort_keys=True, separators=(",", ":"))

@@ -445,3 +445,15 @@ def test_reconcile(P, kfd, tmp_path):
     got = P.labeller.Reconcile(node, new)
     assert got == {**REMOVE_OLD_CASES[0][1], **new} and "beta.amd.com/gpu.family.HPC" not in got
     assert P.labeller.Reconcile(None, new) == new
+
+
+def test_node_label_merge_patch(P):
+    import json
+    before = dict(REMOVE_OLD_CASES[0][0])
+    after = P.labeller.Reconcile(dict(before), {"amd.com/gpu.vram": "179G", "beta.amd.com/gpu.vram": "179G",
+                                                "beta.amd.com/gpu.vram.179G": "8"})
+    patch = json.loads(P.labeller.node_label_merge_patch(before, after))["metadata"]["labels"]
+    applied = {k: v for k, v in {**before, **patch}.items() if v is not None}
+    assert applied == after
+    assert patch["amd.com/gpu.family"] is None and patch["amd.com/gpu.vram"] == "179G" and "dummyLabel1" not in patch
+    assert P.labeller.node_label_merge_patch(after, after) == '{"metadata":{"labels":{}}}'
