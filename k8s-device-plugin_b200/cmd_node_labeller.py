@@ -10,7 +10,7 @@ import json
 import sys
 
 from .context import Context
-from .labeller import Reconcile, generateLabels, labelGeneratorNames
+from .labeller import Reconcile, generateLabels, labelGeneratorNames, node_label_merge_patch
 
 
 def main(argv=None):
@@ -22,10 +22,16 @@ def main(argv=None):
     ap.add_argument("-backend", default="cuda:")
     ap.add_argument("-reconcile", action="store_true",
                     help="read the node's current labels (JSON object) from stdin and print the reconciled map")
+    ap.add_argument("-patch", action="store_true",
+                    help="like -reconcile, but print the JSON merge patch (kubectl patch node $DS_NODE_NAME --type merge -p ...)")
     args = ap.parse_args(argv)
     enabled = {k: bool(getattr(args, k.replace("-", "_"))) for k in names}
     with Context(args.backend) as ctx:
         labels = generateLabels(ctx, enabled)
+    if args.patch:
+        node = json.load(sys.stdin)
+        sys.stdout.write(node_label_merge_patch(node, Reconcile(dict(node), labels)) + "\n")
+        return 0
     if args.reconcile:
         node = json.load(sys.stdin)
         labels = Reconcile(node, labels)
