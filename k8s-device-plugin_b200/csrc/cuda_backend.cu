@@ -570,17 +570,18 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         if (state[i] == 3) { o.bytes = 0; o.healthy = be->gpus[i]->last_healthy; continue; }  // skipped: last verdict stands
         const ProbeJobResult& r = *res[i];
         o.seed = r.seed;
+        if (r.ce != cudaSuccess) {
+            o.err = B2DP_E_CUDA; o.healthy = 0;
+            be->gpus[i]->last_healthy = 0;
+            err = cuda_err("probe", r.ce) + " on " + be->gpus[i]->dev.id;
+            continue;
+        }
         if (r.n_vec == n_vec) o.expected_checksum = expected_checksum(bc, n_words, r.seed);
         else {
             std::array<unsigned long long, 32> bcs;
             if (get_bitcounts(be, r.n_vec * 4, bcs, err) != B2DP_OK) { o.err = B2DP_E_CUDA; o.healthy = 0; continue; }
             o.expected_checksum = expected_checksum(bcs, r.n_vec * 4, r.seed);
             o.bytes = 2ull * r.n_vec * 16;
-        }
-        if (r.ce != cudaSuccess) {
-            o.err = B2DP_E_CUDA; o.healthy = 0;
-            err = cuda_err("probe", r.ce) + " on " + be->gpus[i]->dev.id;
-            continue;
         }
         o.checksum = r.out.checksum;
         o.mismatches = r.out.mismatches;
