@@ -319,6 +319,9 @@ B2DP_API int b2dp_p2p_matrix(b2dp_ctx *ctx, const b2dp_p2p_opts *opts, float *gb
 B2DP_API int b2dp_export_kfd_tree(b2dp_ctx *ctx, const char *dir);
 
 /* ---- node labeller (cmd/k8s-node-labeller/main.go) -------------------------------- */
+/* main.go:37-40: the label/resource domain, "amd.com" (and "beta.amd.com") in the reference and by
+ * default here.  Process-wide; set once at start-up to publish under another vendor domain. */
+B2DP_API int b2dp_set_vendor_domain(const char *domain);
 /* main.go:87-108 createLabels(kind, entries).  Output sorted by key. */
 B2DP_API int b2dp_create_labels(const char *kind, const b2dp_kv_count *entries, int n_entries, b2dp_label *out, int cap, int *n);
 /* main.go:46-53 initLabelLists: the 12 generator names, sorted ("compute-memory-partition", ...). */

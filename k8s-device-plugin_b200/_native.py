@@ -149,6 +149,7 @@ SIGNATURES = {
     "b2dp_preferred_allocation": (_i, [_vp, _strs, _i, _strs, _i, _i, _P(Id64), _i, _ip]),
     "b2dp_p2p_matrix": (_i, [_vp, _P(P2pOpts), _P(C.c_float), _i32p, _P(C.c_uint64), _i]),
     "b2dp_export_kfd_tree": (_i, [_vp, _cp]),
+    "b2dp_set_vendor_domain": (_i, [_cp]),
     "b2dp_create_labels": (_i, [_cp, _P(KvCount), _i, _P(Label), _i, _ip]),
     "b2dp_label_generator_names": (_i, [_P(Id64), _i, _ip]),
     "b2dp_generate_labels": (_i, [_vp, _cp, _P(Label), _i, _ip]),

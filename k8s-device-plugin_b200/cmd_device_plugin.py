@@ -29,6 +29,8 @@ def main(argv=None):
     ap.add_argument("-resource_naming_strategy", default="single",
                     help="Resource strategy to be used: single or mixed")                               # main.go:110
     ap.add_argument("-backend", default="cuda:", help="libb200dp backend uri (cuda:[opts] | kfd:<sysroot>)")
+    ap.add_argument("-resource_namespace", default="amd.com",
+                    help="vendor domain of the resources (amd.com/gpu keeps the reference's names; e.g. nvidia.com)")
     ap.add_argument("-plugin_dir", default=v1beta1.DevicePluginPath)
     ap.add_argument("-start_retry_wait", type=float, default=3.0, help="seconds between plugin start attempts")
     args = ap.parse_args(argv)
@@ -37,6 +39,8 @@ def main(argv=None):
     except ValueError as e:
         print(e, file=sys.stderr)
         return 1
+    from . import plugin as _plugin
+    _plugin.RESOURCE_NAMESPACE = args.resource_namespace        # plugin.go:406-408 returns "amd.com"
     ctx = Context(args.backend)
     lister = AMDGPULister(ctx)
     try:

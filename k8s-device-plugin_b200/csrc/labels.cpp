@@ -12,8 +12,12 @@
 
 namespace b2dp {
 
-static const char kExpPrefix[] = "beta.amd.com";  // main.go:38
-static const char kPrefix[] = "amd.com";          // main.go:39
+// main.go:38-39: amdPrefix = "amd.com", experimentalAMDPrefix = "beta.amd.com".  The domain is
+// a process-wide setting (b2dp_set_vendor_domain) so a deployment can publish e.g. nvidia.com/gpu.*
+// labels; the default keeps the reference's keys.
+static std::mutex g_domain_mu;
+static std::string g_domain = "amd.com";
+static std::string domain() { std::lock_guard<std::mutex> g(g_domain_mu); return g_domain; }
 
 // sorted; main.go:115-379 map keys
 const char* const kGeneratorNames[12] = {
@@ -21,7 +25,7 @@ const char* const kGeneratorNames[12] = {
     "driver-version", "family", "firmware", "memory-partitioning-supported", "product-name", "simd-count", "vram"};
 
 static std::string label_prefix(const std::string& name, bool experimental) {  // main.go:76-85
-    return std::string(experimental ? kExpPrefix : kPrefix) + "/gpu." + name;
+    return (experimental ? "beta." + domain() : domain()) + "/gpu." + name;
 }
 
 void create_labels(const std::string& kind, const std::map<std::string, int>& entries,
@@ -241,6 +245,13 @@ extern "C" int b2dp_create_labels(const char* kind, const b2dp_kv_count* entries
     std::map<std::string, std::string> m;
     create_labels(kind, e, m);
     return emit_labels(m, out, cap, n);
+}
+
+extern "C" int b2dp_set_vendor_domain(const char* d) {
+    if (!d || !*d || strlen(d) > 63 || strchr(d, '/')) return B2DP_E_INVAL;
+    std::lock_guard<std::mutex> g(g_domain_mu);
+    g_domain = d;
+    return B2DP_OK;
 }
 
 extern "C" int b2dp_label_generator_names(char (*names)[64], int cap, int* n) {

@@ -12,9 +12,20 @@ def labelGeneratorNames() -> List[str]:
     return [N.s(arr[i].value) for i in range(n)]
 
 
+_domain = "amd.com"      # main.go:39 amdPrefix; "beta." + it is experimentalAMDPrefix (main.go:38)
+
+
+def setVendorDomain(domain: str) -> None:
+    """Publish labels (and, via plugin.RESOURCE_NAMESPACE, resources) under another vendor domain;
+    the default "amd.com" keeps the reference's keys."""
+    global _domain
+    N.check(N.lib.b2dp_set_vendor_domain(domain.encode()))
+    _domain = domain
+
+
 def createLabelPrefix(name: str, experimental: bool) -> str:
     """main.go:76-85."""
-    return "%s/gpu.%s" % ("beta.amd.com" if experimental else "amd.com", name)
+    return "%s/gpu.%s" % ("beta." + _domain if experimental else _domain, name)
 
 
 def createLabels(kind: str, entries: Dict[str, int]) -> Dict[str, str]:

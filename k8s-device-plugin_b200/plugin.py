@@ -125,7 +125,8 @@ class AMDGPULister:
         self.Heartbeat: "queue.Queue" = queue.Queue()
 
     def GetResourceNamespace(self) -> str:
-        return RESOURCE_NAMESPACE
+        import sys
+        return sys.modules[__name__].RESOURCE_NAMESPACE
 
     def NewPlugin(self, resourceLastName: str) -> AMDGPUPlugin:
         return AMDGPUPlugin(self.ctx, resourceLastName, self.Heartbeat)

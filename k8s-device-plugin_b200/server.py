@@ -16,7 +16,8 @@ import grpc
 from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
 
 from . import v1beta1
-from .plugin import RESOURCE_NAMESPACE, AMDGPUPlugin, PluginError
+from . import plugin as _plugin
+from .plugin import AMDGPUPlugin, PluginError
 
 _ident = lambda b: b  # noqa: E731
 
@@ -70,10 +71,10 @@ class PluginServer:
                  kubelet_socket: str = None):
         self.plugin = plugin
         self.plugin_dir = plugin_dir
-        self.endpoint = "%s_%s" % (RESOURCE_NAMESPACE, plugin.Resource)           # dpm/plugin.go:51-59
+        self.endpoint = "%s_%s" % (_plugin.RESOURCE_NAMESPACE, plugin.Resource)           # dpm/plugin.go:51-59
         self.socket_path = os.path.join(plugin_dir, self.endpoint)
         self.kubelet_socket = kubelet_socket or os.path.join(plugin_dir, "kubelet.sock")
-        self.resource_name = "%s/%s" % (RESOURCE_NAMESPACE, plugin.Resource)
+        self.resource_name = "%s/%s" % (_plugin.RESOURCE_NAMESPACE, plugin.Resource)
         self._server = None
 
     def start(self):

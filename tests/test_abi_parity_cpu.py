@@ -457,3 +457,16 @@ def test_node_label_merge_patch(P):
     assert applied == after
     assert patch["amd.com/gpu.family"] is None and patch["amd.com/gpu.vram"] == "179G" and "dummyLabel1" not in patch
     assert P.labeller.node_label_merge_patch(after, after) == '{"metadata":{"labels":{}}}'
+
+
+def test_vendor_domain_is_configurable(P):
+    try:
+        P.labeller.setVendorDomain("nvidia.com")
+        assert P.labeller.createLabels("vram", {"179G": 8}) == {
+            "beta.nvidia.com/gpu.vram.179G": "8", "beta.nvidia.com/gpu.vram": "179G", "nvidia.com/gpu.vram": "179G"}
+        assert P.labeller.removeOldNodeLabels({"nvidia.com/gpu.vram": "1G", "amd.com/gpu.vram": "1G"}) == {"amd.com/gpu.vram": "1G"}
+        with pytest.raises(P._native.B2dpError):
+            P.labeller.setVendorDomain("bad/domain")
+    finally:
+        P.labeller.setVendorDomain("amd.com")
+    assert P.labeller.createLabelPrefix("vram", True) == "beta.amd.com/gpu.vram"
