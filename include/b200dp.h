@@ -253,6 +253,20 @@ typedef struct b2dp_cycle_stats {
 B2DP_API int b2dp_list_and_watch(b2dp_ctx *ctx, const char *resource, const b2dp_cycle_opts *opts, uint8_t *buf, size_t cap,
                         size_t *len, b2dp_cycle_stats *stats);
 
+/* The ListAndWatch loop itself, owned by the library (plugin.go:229-330 + the `-pulse` ticker of
+ * cmd/k8s-device-plugin/main.go:129-137): a thread sends the initial list, then one heartbeat cycle per
+ * tick -- every pulse_ms (0 = no ticker) and on every b2dp_watch_beat() (the reference's
+ * `l.Heartbeat <- true`) -- until b2dp_watch_stop() (the reference's p.signal).  Each send invokes
+ * `cb(user, rc, buf, len, stats)` on that thread with the serialized ListAndWatchResponse (valid
+ * during the call); rc != 0 reports a failed cycle.  `opts` as for b2dp_list_and_watch (the
+ * INITIAL/HEARTBEAT bits are set by the loop). */
+typedef void (*b2dp_watch_cb)(void *user, int rc, const uint8_t *buf, size_t len, const b2dp_cycle_stats *stats);
+typedef struct b2dp_watch b2dp_watch;
+B2DP_API int b2dp_watch_start(b2dp_ctx *ctx, const char *resource, uint32_t pulse_ms, const b2dp_cycle_opts *opts,
+                     b2dp_watch_cb cb, void *user, b2dp_watch **out);
+B2DP_API int b2dp_watch_beat(b2dp_watch *w);
+B2DP_API void b2dp_watch_stop(b2dp_watch *w);
+
 /* plugin.go:356-393 Allocate for one container request: "/dev/kfd" first, then the two
  * /dev/dri paths of every known id (card, then renderD); unknown ids add nothing.
  * cuda backend: /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools, then /dev/nvidia<minor>. */

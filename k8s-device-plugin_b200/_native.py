@@ -104,6 +104,8 @@ if not os.path.exists(LIB_PATH):
         "(or `make -C k8s-device-plugin_b200/csrc`). There is no CPU fallback.")
 lib = C.CDLL(LIB_PATH)
 
+WatchCb = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(CycleStats))
+
 _P = C.POINTER
 _vp, _cp, _i, _ip = C.c_void_p, C.c_char_p, C.c_int, _P(C.c_int)
 _i32p, _u8p, _szp = _P(C.c_int32), _P(C.c_uint8), _P(C.c_size_t)
@@ -134,6 +136,9 @@ SIGNATURES = {
     "b2dp_probe_peek": (_i, [_vp, _i, C.c_uint64, _P(C.c_uint32), C.c_uint64]),
     "b2dp_merge_health": (_i, [_P(Id64), _i, C.c_int32, _i, _P(Id64), _i32p, _i, _i32p]),
     "b2dp_list_and_watch": (_i, [_vp, _cp, _P(CycleOpts), _u8p, C.c_size_t, _szp, _P(CycleStats)]),
+    "b2dp_watch_start": (_i, [_vp, _cp, C.c_uint32, _P(CycleOpts), WatchCb, _vp, _P(_vp)]),
+    "b2dp_watch_beat": (_i, [_vp]),
+    "b2dp_watch_stop": (None, [_vp]),
     "b2dp_device_specs": (_i, [_vp, _strs, _i, _P(DevSpec), _i, _ip]),
     "b2dp_allocate_response": (_i, [_vp, _strs, _i, _u8p, C.c_size_t, _szp]),
     "b2dp_allocator_new": (_i, [_P(_vp)]),

@@ -166,6 +166,11 @@ class Context:
                            st.probe_bytes, st.ms_link_check, st.n_link_faults)
         return wire, stats
 
+    def watch(self, callback, resource: str = "gpu", pulse_ms: int = 0, flags: int = 0, timeout_ms=0, min_gbs=0.0):
+        """Start the library-owned ListAndWatch loop (b2dp_watch_start).  `callback(rc, wire, stats)`
+        runs on the library's thread for the initial list and every heartbeat.  Returns a Watch."""
+        return Watch(self, callback, resource, pulse_ms, flags, timeout_ms, min_gbs)
+
     # ---- Allocate ------------------------------------------------------------------------
     def device_specs(self, ids: List[str]):
         arr_in = N.str_array(ids)
@@ -222,3 +227,31 @@ class Context:
                                  lambda a, cap, pn: N.lib.b2dp_generate_labels(self._h, csv, a, cap, pn))
         N.check(rc, self._h)
         return {N.s(x.key): N.s(x.value) for x in arr[:n]}
+
+
+class Watch:
+    """Handle of a native ListAndWatch loop: beat() = one heartbeat tick, stop() ends the stream."""
+
+    def __init__(self, ctx: Context, callback, resource, pulse_ms, flags, timeout_ms, min_gbs):
+        opts = N.CycleOpts()
+        opts.flags = flags
+        opts.probe = N.ProbeOpts(timeout_ms, 0, min_gbs, 0)
+
+        def tramp(_user, rc, buf, ln, st):
+            s = st.contents
+            stats = CycleStats(s.n_devices, s.n_unhealthy, bool(s.homogeneous), bool(s.node_healthy), s.ms_total,
+                               s.ms_enumerate, s.ms_probe, s.ms_encode, s.probe_gbs_min, s.probe_gbs_sum, s.probe_bytes,
+                               s.ms_link_check, s.n_link_faults)
+            callback(rc, bytes(buf[:ln]) if ln else b"", stats)
+        self._cb = N.WatchCb(tramp)          # keep the trampoline alive as long as the loop
+        self._h = C.c_void_p()
+        N.check(N.lib.b2dp_watch_start(ctx._h, resource.encode(), pulse_ms, C.byref(opts), self._cb, None,
+                                       C.byref(self._h)), ctx._h)
+
+    def beat(self):
+        N.check(N.lib.b2dp_watch_beat(self._h))
+
+    def stop(self):
+        if self._h:
+            N.lib.b2dp_watch_stop(self._h)
+            self._h = C.c_void_p()

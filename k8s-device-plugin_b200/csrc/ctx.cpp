@@ -6,6 +6,8 @@
 #include <cerrno>
 #include <chrono>
 #include <climits>
+#include <condition_variable>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -410,6 +412,91 @@ extern "C" int b2dp_list_and_watch(b2dp_ctx* c, const char* resource, const b2dp
     if (!wire.empty() && !buf) return B2DP_E_INVAL;
     memcpy(buf, wire.data(), wire.size());
     return B2DP_OK;
+}
+
+// ---- native ListAndWatch loop ------------------------------------------------------------
+// plugin.go:229-330 as a library-owned thread: the initial list at stream start, then one
+// heartbeat cycle per tick -- from the built-in ticker (cmd/k8s-device-plugin/main.go:129-137,
+// `-pulse`) or from b2dp_watch_beat() (the reference's `l.Heartbeat <- true`) -- until
+// b2dp_watch_stop() (the reference's p.signal, plugin.go:322-329).
+struct b2dp_watch {
+    b2dp_ctx* ctx = nullptr;
+    std::string resource;
+    b2dp_cycle_opts opts{};
+    uint32_t pulse_ms = 0;
+    b2dp_watch_cb cb = nullptr;
+    void* user = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    int pending_beats = 0;
+    bool stop = false;
+};
+
+static void watch_send(b2dp_watch* w, uint32_t flags) {
+    std::vector<uint8_t> buf(1 << 14);
+    b2dp_cycle_opts o = w->opts;
+    o.flags = (o.flags & ~(B2DP_LW_INITIAL | B2DP_LW_HEARTBEAT)) | flags;
+    size_t len = 0;
+    b2dp_cycle_stats st{};
+    int rc = b2dp_list_and_watch(w->ctx, w->resource.c_str(), &o, buf.data(), buf.size(), &len, &st);
+    if (rc == B2DP_E_NOSPC) {
+        buf.resize(len);
+        rc = b2dp_list_and_watch(w->ctx, w->resource.c_str(), &o, buf.data(), buf.size(), &len, &st);
+    }
+    // plugin.go:296-298: a heterogeneous node with no devices of this resource sends nothing
+    if (rc == B2DP_OK && (st.n_devices || st.homogeneous)) w->cb(w->user, rc, buf.data(), len, &st);
+    else if (rc != B2DP_OK) w->cb(w->user, rc, nullptr, 0, &st);
+}
+
+static void watch_loop(b2dp_watch* w) {
+    watch_send(w, B2DP_LW_INITIAL);
+    auto next = std::chrono::steady_clock::now() + std::chrono::milliseconds(w->pulse_ms);
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> l(w->mu);
+            auto pred = [&] { return w->stop || w->pending_beats > 0; };
+            if (w->pulse_ms) {
+                if (!w->cv.wait_until(l, next, pred)) {  // ticker fired
+                    next += std::chrono::milliseconds(w->pulse_ms);
+                    w->pending_beats++;
+                }
+            } else w->cv.wait(l, pred);
+            if (w->stop) return;
+            w->pending_beats--;
+        }
+        watch_send(w, B2DP_LW_HEARTBEAT);
+    }
+}
+
+extern "C" int b2dp_watch_start(b2dp_ctx* c, const char* resource, uint32_t pulse_ms, const b2dp_cycle_opts* opts,
+                                b2dp_watch_cb cb, void* user, b2dp_watch** out) {
+    if (!c || !cb || !out) return B2DP_E_INVAL;
+    auto* w = new b2dp_watch();
+    w->ctx = c;
+    w->resource = resource ? resource : "gpu";
+    if (opts) w->opts = *opts;
+    w->pulse_ms = pulse_ms;
+    w->cb = cb;
+    w->user = user;
+    w->th = std::thread(watch_loop, w);
+    *out = w;
+    return B2DP_OK;
+}
+
+extern "C" int b2dp_watch_beat(b2dp_watch* w) {
+    if (!w) return B2DP_E_INVAL;
+    { std::lock_guard<std::mutex> l(w->mu); w->pending_beats++; }
+    w->cv.notify_one();
+    return B2DP_OK;
+}
+
+extern "C" void b2dp_watch_stop(b2dp_watch* w) {
+    if (!w) return;
+    { std::lock_guard<std::mutex> l(w->mu); w->stop = true; }
+    w->cv.notify_all();
+    if (w->th.joinable()) w->th.join();
+    delete w;
 }
 
 // ---- Allocate ----------------------------------------------------------------------------
