@@ -302,3 +302,24 @@ def test_word_index_wraps_past_16_gib(P):
         ctx.probe_inject_fault(0, (1 << 32) + 5, 0x80)
         (r,) = ctx.probe_health()
         assert (r.mismatches, r.first_bad_word, r.healthy) == (1, (1 << 32) + 5, False)
+
+
+def test_native_watch_loop_on_cuda(P):
+    """b2dp_watch_*: the library's own thread runs stream start + a 20 ms heartbeat ticker with the
+    GPU probe in every tick; an injected fault shows up in exactly one response."""
+    import queue
+    got = queue.Queue()
+    with _open(P, 64 * MiB) as ctx:
+        w = ctx.watch(lambda rc, wire, st: got.put((rc, wire, st)), pulse_ms=20, min_gbs=1e-3)
+        rc, wire, st = got.get(timeout=10)
+        assert rc == 0 and st.probe_bytes == 0                      # stream start: no probe, all Healthy
+        assert [d.health for d in P.v1beta1.ListAndWatchResponse.FromString(wire).devices] == ["Healthy"]
+        healths = []
+        for i in range(6):
+            if i == 2:
+                ctx.probe_inject_fault(0, 777, 0x10)
+            rc, wire, st = got.get(timeout=10)
+            assert rc == 0 and st.probe_bytes == 2 * 64 * MiB
+            healths.append(P.v1beta1.ListAndWatchResponse.FromString(wire).devices[0].health)
+        w.stop()
+        assert healths.count("Unhealthy") == 1 and healths[0] == "Healthy" and healths[-1] == "Healthy", healths
