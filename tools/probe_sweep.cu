@@ -49,6 +49,10 @@ template <int CW, int TV, int ST, int HINT = 0> static void launch_tma(const uin
     hbm_probe_tma<CW, TV, ST, HINT><<<grid, (CW + 1) * 32, smem, st>>>(s, d, n, seed, delta, c, o, seq);
 }
 
+static unsigned int g_period_ns = 0;
+template <int CW, int TV, int ST> static void launch_phased(const uint4* s, uint4* d, unsigned long long n, uint32_t seed,
+    uint32_t delta, ProbeCtl* c, ProbeOut* o, unsigned long long seq, int grid, cudaStream_t st);
+
 __global__ void plain_copy(const uint4* __restrict__ s, uint4* __restrict__ d, unsigned long long n) {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) d[i] = s[i];
@@ -115,7 +119,84 @@ __global__ void __launch_bounds__(160) read_only_tma(const uint4* __restrict__ s
     if (acc == 0x123456789abcdefull) *sink = acc;
 }
 
+// ---- experiment: chip-wide read/write phase separation (tool-only) ----------------------------
+// Pure reads run at 7.08 TB/s and pure writes at 7.07 TB/s on this part, a mixed copy at 6.49.
+// Here every CTA (1 per SM, a 12 x 16 KiB ring) alternates "load the whole ring" / "store the
+// whole ring", and the two windows are aligned across the chip with %globaltimer (period_ns;
+// 0 = free-running batches).  Measures whether SM-side phasing can lift the mixed-copy ceiling.
+template <int CW, int TILE_VEC, int STAGES>
+__global__ void __launch_bounds__((CW + 1) * 32)
+hbm_probe_phased(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned long long n_vec, uint32_t seed,
+                 uint32_t delta, ProbeCtl* ctl, ProbeOut* out, unsigned long long seq, unsigned int period_ns) {
+    constexpr int THREADS = (CW + 1) * 32, CT = CW * 32, PER_THREAD = TILE_VEC / CT;
+    constexpr uint32_t TILE_BYTES = TILE_VEC * 16u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4* tiles = reinterpret_cast<uint4*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * TILE_BYTES);
+    uint64_t* done = full + STAGES;
+    const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long n_tiles = n_vec / TILE_VEC;
+    const unsigned long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], CT); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+    Acc a;
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            unsigned int batch = 0;
+            for (unsigned long long k0 = 0; k0 < my_tiles; k0 += STAGES, ++batch) {
+                const int nb = (int)(my_tiles - k0 < (unsigned long long)STAGES ? my_tiles - k0 : STAGES);
+                if (period_ns) while ((globaltimer_ns() % period_ns) >= period_ns / 2) { }   // READ window
+                for (int j = 0; j < nb; ++j) {
+                    mbar_expect_tx(&full[j], TILE_BYTES);
+                    bulk_g2s(tiles + (size_t)j * TILE_VEC, src + (blockIdx.x + (k0 + j) * gridDim.x) * TILE_VEC, TILE_BYTES, &full[j]);
+                }
+                if (period_ns) while ((globaltimer_ns() % period_ns) < period_ns / 2) { }    // WRITE window
+                for (int j = 0; j < nb; ++j) {
+                    mbar_wait(&done[j], batch & 1u);
+                    bulk_s2g(dst + (blockIdx.x + (k0 + j) * gridDim.x) * TILE_VEC, tiles + (size_t)j * TILE_VEC, TILE_BYTES);
+                }
+                bulk_commit();
+                bulk_wait_read<0>();
+            }
+            bulk_wait_all<0>();
+        }
+    } else {
+        const int ct = threadIdx.x - 32;
+        unsigned int batch = 0;
+        for (unsigned long long k0 = 0; k0 < my_tiles; k0 += STAGES, ++batch) {
+            const int nb = (int)(my_tiles - k0 < (unsigned long long)STAGES ? my_tiles - k0 : STAGES);
+            for (int j = 0; j < nb; ++j) {
+                mbar_wait(&full[j], batch & 1u);
+                uint4* tile = tiles + (size_t)j * TILE_VEC;
+                const unsigned long long t = blockIdx.x + (k0 + j) * gridDim.x;
+                uint4 v[PER_THREAD];
+#pragma unroll
+                for (int u = 0; u < PER_THREAD; ++u) v[u] = tile[ct + u * CT];
+#pragma unroll
+                for (int u = 0; u < PER_THREAD; ++u) { check4(v[u], t * TILE_VEC + ct + u * CT, seed, delta, a); tile[ct + u * CT] = v[u]; }
+                fence_proxy_async_smem();
+                mbar_arrive(&done[j]);
+            }
+        }
+    }
+    for (unsigned long long i = n_tiles * TILE_VEC + (unsigned long long)blockIdx.x * THREADS + threadIdx.x; i < n_vec;
+         i += (unsigned long long)gridDim.x * THREADS) { uint4 v = ldg_na(src + i); check4(v, i, seed, delta, a); stg_na(dst + i, v); }
+    finish<THREADS>(a, ctl, out, seq, t0);
+}
+
 struct Cfg { std::string name; LaunchFn fn; int ctas_per_sm; };
+
+template <int CW, int TV, int ST> static void launch_phased(const uint4* s, uint4* d, unsigned long long n, uint32_t seed,
+    uint32_t delta, ProbeCtl* c, ProbeOut* o, unsigned long long seq, int grid, cudaStream_t st) {
+    constexpr size_t smem = (size_t)ST * TV * 16 + 2 * ST * 8;
+    static bool once = false;
+    if (!once) { CK(cudaFuncSetAttribute(hbm_probe_phased<CW, TV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once = true; }
+    hbm_probe_phased<CW, TV, ST><<<grid, (CW + 1) * 32, smem, st>>>(s, d, n, seed, delta, c, o, seq, g_period_ns);
+}
 
 int main(int argc, char** argv) {
     unsigned long long bytes = 1ull << 30;
@@ -209,7 +290,31 @@ int main(int argc, char** argv) {
         printf("memset,0,0,%.4f,%.4f,%.1f,%.1f,1\n", rm.first, rm.second, 1.0 * bytes / rm.first / 1e6, 1.0 * bytes / rm.second / 1e6);
     }
 
+    // phased experiment: name encodes the period; ctas_per_sm field carries it to the loop below
+    struct PCfg { const char* name; LaunchFn fn; };
+    const PCfg pc[] = {{"phased_cw8_tv1024_st12", launch_phased<8, 1024, 12>}, {"phased_cw8_tv1024_st8", launch_phased<8, 1024, 8>},
+                       {"phased_cw8_tv2048_st6", launch_phased<8, 2048, 6>}};
     unsigned long long seq = 0;
+    if (!only || strstr(only, "phased")) {
+        for (auto& p : pc)
+            for (unsigned int per : {0u, 6000u, 7000u, 8000u, 9000u, 10000u, 12000u, 16000u}) {
+                g_period_ns = per;
+                auto body = [&] {
+                    const uint32_t next = B.seed * 1664525u + 1013904223u;
+                    const uint4* s = B.cur == 0 ? B.a : B.b; uint4* d = B.cur == 0 ? B.b : B.a;
+                    p.fn(s, d, B.n_vec, B.seed, B.seed ^ next, B.ctl, B.out_d, ++seq, sms, st);
+                    B.seed = next; B.cur ^= 1;
+                };
+                const uint32_t seed_before = B.seed;
+                body();
+                CK(cudaStreamSynchronize(st));
+                const bool ok = B.out_h->seq == seq && B.out_h->mismatches == 0 && B.out_h->checksum == cpu_checksum(B.n_vec * 4, seed_before);
+                auto r = time_it(body);
+                printf("%s_period%u,1,%d,%.4f,%.4f,%.1f,%.1f,%d\n", p.name, per, sms, r.first, r.second,
+                       2.0 * bytes / r.first / 1e6, 2.0 * bytes / r.second / 1e6, ok ? 1 : 0);
+                fflush(stdout);
+            }
+    }
     for (auto& c : cfgs) {
         if (only && c.name.find(only) == std::string::npos) continue;
         const int grid = sms * c.ctas_per_sm;
