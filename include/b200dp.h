@@ -271,7 +271,9 @@ B2DP_API void b2dp_watch_stop(b2dp_watch *w);
  * /dev/dri paths of every known id (card, then renderD); unknown ids add nothing.
  * cuda backend: /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools, then /dev/nvidia<minor>. */
 B2DP_API int b2dp_device_specs(b2dp_ctx *ctx, const char *const *ids, int n_ids, b2dp_devspec *out, int cap, int *n);
-/* Same, serialized as v1beta1.ContainerAllocateResponse (api.proto: devices=3). */
+/* Same, serialized as v1beta1.ContainerAllocateResponse (api.proto: devices=3).  The cuda backend also sets
+ * envs["NVIDIA_VISIBLE_DEVICES"] = the allocated /dev/nvidia minors ("void" if none); the kfd backend sets
+ * no envs, like the reference. */
 B2DP_API int b2dp_allocate_response(b2dp_ctx *ctx, const char *const *ids, int n_ids, uint8_t *buf, size_t cap, size_t *len);
 
 /* ---- allocator (internal/pkg/allocator) ------------------------------------------ */

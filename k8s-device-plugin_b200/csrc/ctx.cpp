@@ -546,6 +546,22 @@ extern "C" int b2dp_allocate_response(b2dp_ctx* c, const char* const* ids, int n
     int rc = device_specs(c, ids, n_ids, specs);
     if (rc != B2DP_OK) return rc;
     std::string wire;
+    if (c->kind == b2dp_ctx::CUDA) {
+        // The reference's Allocate sets no envs (plugin.go:356-393).  On NVIDIA nodes the container
+        // runtime hook selects GPUs from NVIDIA_VISIBLE_DEVICES, so the cuda backend also names the
+        // allocated devices there (envs = field 1, map<string,string>).
+        std::vector<Device> devs;
+        rc = enumerate_ctx(c, devs);
+        if (rc != B2DP_OK) return rc;
+        std::string list;
+        for (int i = 0; i < n_ids; ++i)
+            for (const auto& d : devs)
+                if (ids[i] && d.id == ids[i]) { list += (list.empty() ? "" : ",") + std::to_string(d.card); break; }
+        std::string entry;
+        pb::string_field(entry, 1, "NVIDIA_VISIBLE_DEVICES");
+        pb::string_field(entry, 2, list.empty() ? "void" : list);
+        pb::bytes_field(wire, 1, entry);
+    }
     for (auto& s : specs) pb::encode_devspec(wire, 3, s.container_path, s.host_path, s.permissions);
     *len = wire.size();
     if (wire.size() > cap) return B2DP_E_NOSPC;

@@ -170,6 +170,9 @@ def test_cuda_backend_equals_reference_algorithm_on_exported_tree(P, tmp_path):
         assert got == olab.generateLabels({g: True for g in gens}, root)
         assert got["amd.com/gpu.cu-count"] == "148" and got["amd.com/gpu.product-name"] == "NVIDIA_B200"
         # Allocate: the NVIDIA device nodes exist on the box
+        resp = P.v1beta1.ContainerAllocateResponse.FromString(ctx.allocate_response([ids[0], "unknown"]))
+        assert dict(resp.envs) == {"NVIDIA_VISIBLE_DEVICES": str(devs[ids[0]]["card"])}
+        assert [d.host_path for d in resp.devices][-1] == "/dev/nvidia%d" % devs[ids[0]]["card"]
         specs = ctx.device_specs(ids)
         assert [s[0] for s in specs[:3]] == ["/dev/nvidiactl", "/dev/nvidia-uvm", "/dev/nvidia-uvm-tools"]
         assert len(specs) == 3 + len(ids)
