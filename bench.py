@@ -319,6 +319,17 @@ def main():
     msg = pkg.v1beta1.ListAndWatchResponse.FromString(wire)
     assert len(msg.devices) == 1 and msg.devices[0].health == "Healthy", msg
 
+    # ---- stream start: the initial ListAndWatch list (enumerate + homogeneity + encode; the reference does
+    # two GetAMDGPUs() walks here, plugin.go:231,237) -- reported next to reference_cpu_path ------
+    starts = []
+    for i in range(60):
+        t0 = time.perf_counter()
+        ctx.list_and_watch("gpu", N.LW_INITIAL)
+        if i >= 10:
+            starts.append((time.perf_counter() - t0) * 1e3)
+    starts.sort()
+    stream_start_ms = max_over_ranks(starts[len(starts) // 2])
+
     # ---- the kubelet's view: heartbeat tick -> ListAndWatchResponse received over the plugin's unix
     # socket (grpcio server + client stream in this process); informative, not the timed `e2e` ------
     grpc_ms = None
@@ -373,6 +384,7 @@ def main():
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 48 * 1 + len(wire),
                 "cycle_ms": round(t_e2e / args.steps * 1e3, 4), "ms_enumerate": round(enum_ms / args.steps, 5),
                 "ms_encode": round(enc_ms / args.steps, 5), "response_bytes": len(wire),
+                "stream_start_ms": round(stream_start_ms, 4),
                 "heartbeat_to_kubelet_grpc_ms": None if grpc_ms is None or grpc_ms < 0 else round(grpc_ms, 4),
                 "note": "no bulk host buffers on this path: kernel arguments in, 48-byte result block (pinned mapped) + serialized response out"},
         "gpu_launches": args.steps * n,

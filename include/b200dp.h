@@ -126,7 +126,10 @@ typedef struct b2dp_ctx b2dp_ctx;
  *   "kfd:<sysroot>"   parity mode: <sysroot> plays "/" and holds sys/module/amdgpu/drivers,
  *                     sys/class/kfd/kfd/topology, sys/devices/platform/amdgpu_xcp_*; no GPU work.
  *   "cuda:[k=v,...]"  real B200s.  keys: devices=0+1+2 (default all), bytes=<S per buffer,
- *                     default 1073741824>, min_gbs=<health threshold, default 3000>,
+ *                     default 1073741824>, slots=<buffers in the probe ring, default 2 = ping-pong; with M
+ *                     slots pass k verifies slot k mod M (written by pass k-1) and re-keys it into slot
+ *                     k+1 mod M, so M heartbeats scrub M*S bytes of HBM>,
+ *                     min_gbs=<health threshold, default 3000>,
  *                     sysroot=<dir for numa_node lookups, default "/">, p2p_bytes=<default 268435456>,
  *                     busy=probe|skip|shrink (what to do on a GPU another process is using; default probe),
  *                     shrink_bytes=<prefix verified by busy=shrink, default 67108864>, ecc=1 (also fail on new

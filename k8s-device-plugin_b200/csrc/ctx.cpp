@@ -132,6 +132,7 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
                     pos = e + 1;
                 }
             } else if (p.first == "bytes") cfg.bytes = strtoull(p.second.c_str(), nullptr, 0);
+            else if (p.first == "slots") cfg.slots = atoi(p.second.c_str());
             else if (p.first == "p2p_bytes") cfg.p2p_bytes = strtoull(p.second.c_str(), nullptr, 0);
             else if (p.first == "min_gbs") cfg.min_gbs = (float)atof(p.second.c_str());
             else if (p.first == "sysroot") cfg.sysroot = p.second;
@@ -145,6 +146,7 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else return fail(B2DP_E_INVAL, "unknown cuda: option " + p.first);
         }
         if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");
+        if (cfg.slots < 2 || cfg.slots > 4096) return fail(B2DP_E_INVAL, "slots must be in [2, 4096]");
         std::string err;
         CudaBackend* be = nullptr;
         int rc = cuda_backend_open(cfg, &be, err);

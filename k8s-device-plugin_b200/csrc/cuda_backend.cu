@@ -116,13 +116,14 @@ struct Gpu {
     std::deque<std::function<void()>> q;
     bool quit = false;
     // state owned by the worker thread
-    uint4* buf[2] = {nullptr, nullptr};
+    std::vector<uint4*> buf;            // ring of cfg.slots buffers: pass k reads buf[cur], writes buf[next()]
     ProbeCtl* ctl = nullptr;
     ProbeOut *out_h = nullptr, *out_d = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     uint32_t seed = 0;
     int cur = 0;
+    int next() const { return (cur + 1) % (int)buf.size(); }
     unsigned long long seq = 0;
     std::atomic<bool> inflight{false};  // a timed-out pass is still owned by the worker
     std::vector<char> peer_enabled;
@@ -305,14 +306,14 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         Gpu* g = be->gpus[i].get();
         const unsigned long long bytes = cfg.bytes, n_vec = cfg.bytes / 16;
         const int idx = (int)i;
+        g->buf.assign((size_t)cfg.slots, nullptr);
         cs.push_back(post(g, [g, bytes, n_vec, idx, &errs, &where] {
             cudaError_t e;
 #define TRY(x) if ((e = (x)) != cudaSuccess) { errs[idx] = e; where[idx] = #x; return; }
             TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
             TRY(cudaEventCreate(&g->e0));
             TRY(cudaEventCreate(&g->e1));
-            TRY(cudaMalloc(&g->buf[0], bytes));
-            TRY(cudaMalloc(&g->buf[1], bytes));
+            for (auto& b : g->buf) TRY(cudaMalloc(&b, bytes));
             TRY(cudaMalloc(&g->ctl, sizeof(ProbeCtl)));
             ProbeCtl init{};
             init.first_bad = ~0ull; init.t_start_ns = ~0ull;
@@ -351,8 +352,7 @@ void cuda_backend_close(CudaBackend* be) {
         if (!g->th.joinable()) continue;
         post(g, [g] {
             if (g->stream) cudaStreamSynchronize(g->stream);
-            if (g->buf[0]) cudaFree(g->buf[0]);
-            if (g->buf[1]) cudaFree(g->buf[1]);
+            for (uint4* b : g->buf) if (b) cudaFree(b);
             if (g->ctl) cudaFree(g->ctl);
             if (g->out_h) cudaFreeHost(g->out_h);
             if (g->e0) cudaEventDestroy(g->e0);
@@ -431,7 +431,7 @@ static void probe_issue(Gpu* g, ProbeJobResult* r, unsigned long long n_vec_full
     r->seed = seed;
     r->seq = ++g->seq;
     cudaEventRecord(g->e0, g->stream);
-    launch_probe(g, n_vec, variant, seed, r->advance ? seed ^ next : 0u, g->buf[g->cur], g->buf[g->cur ^ 1], r->seq);
+    launch_probe(g, n_vec, variant, seed, r->advance ? seed ^ next : 0u, g->buf[g->cur], g->buf[g->next()], r->seq);
     r->ce = cudaGetLastError();
     cudaEventRecord(g->e1, g->stream);
 }
@@ -452,7 +452,7 @@ static void probe_collect(Gpu* g, ProbeJobResult* r, unsigned long long n_vec) {
         return;
     }
     g->seed = g->seed * 1664525u + 1013904223u;
-    g->cur ^= 1;
+    g->cur = g->next();
     if (r->out.mismatches != 0 || !r->seq_ok) {
         // report once, then start the next pass from a clean pattern: a transient flip is
         // reported exactly once, a stuck cell shows up again on the next pass
@@ -710,7 +710,7 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
                 // copies cross NVLink, verification happens on the receiving GPU
                 hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>
                     <<<(int)g->sms * kTmaCtasPerSm, (kTmaCW + 1) * 32, kTmaSmem, g->stream>>>(
-                        src, g->buf[g->cur ^ 1], n_vec, seed, 0u, g->ctl, g->out_d, seq);
+                        src, g->buf[g->next()], n_vec, seed, 0u, g->ctl, g->out_d, seq);
                 cudaError_t e = cudaGetLastError();
                 cudaEventRecord(g->e1, g->stream);
                 if (e == cudaSuccess) e = cudaEventSynchronize(g->e1);

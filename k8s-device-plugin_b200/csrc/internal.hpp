@@ -91,6 +91,7 @@ class CudaBackend;
 struct CudaConfig {
     std::vector<int> devices;  // empty = all
     uint64_t bytes = 1ull << 30;
+    int slots = 2;                       // ring of probe buffers per GPU (2 = ping-pong; more = scrub window)
     uint64_t p2p_bytes = 256ull << 20;
     float min_gbs = 3000.f;
     std::string sysroot = "/";

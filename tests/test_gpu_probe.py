@@ -274,6 +274,37 @@ def test_busy_policy_skip_and_shrink(P):
             helper.kill()
 
 
+def test_scrub_ring_rotates_through_all_slots(P):
+    """`slots=M`: pass k verifies slot k mod M and re-keys it into slot k+1 mod M.  Every pass stays
+    bit-exact with the oracle, M*S bytes of HBM are held (and scrubbed once per M heartbeats), a fault
+    poked into the current slot is caught by the next pass only, and M+1 passes later the ring has
+    wrapped over the slot that once held the fault without any residue."""
+    import torch
+    nbytes, slots = 48 * MiB + 16 * 3, 5
+    n_words = nbytes // 4
+    free0, _ = torch.cuda.mem_get_info(0)
+    with _open(P, nbytes, ",slots=%d" % slots) as ctx:
+        free1, _ = torch.cuda.mem_get_info(0)
+        assert free0 - free1 >= slots * (nbytes // MiB) * MiB
+        seed = oprobe.initial_seed(0)
+        for k in range(2 * slots + 3):
+            if k == 2:
+                ctx.probe_inject_fault(0, 12345, 0x10)
+            before = ctx.probe_peek(0, 0, n_words)
+            (r,) = ctx.probe_health(min_gbs=1e-3)
+            cs, bad, first, dst = oprobe.probe_pass(before, seed, oprobe.next_seed(seed))
+            assert (r.seed, r.checksum, r.mismatches, r.first_bad_word) == (seed, cs, bad, first)
+            assert bad == (1 if k == 2 else 0) and r.healthy == (k != 2)
+            seed = oprobe.next_seed(seed)
+            if k != 2:                                                # after a fault the next slot is re-filled clean
+                assert np.array_equal(ctx.probe_peek(0, 0, n_words), dst)
+            else:
+                assert np.array_equal(ctx.probe_peek(0, 0, n_words), oprobe.pattern(n_words, seed))
+    for bad_uri in ("cuda:devices=0,slots=1", "cuda:devices=0,slots=99999"):
+        with pytest.raises(P._native.B2dpError):
+            P.Context(bad_uri)
+
+
 def test_ecc_option_is_harmless(P):
     with _open(P, 16 * MiB, ",ecc=1") as ctx:
         (r,) = ctx.probe_health(min_gbs=1e-3)
