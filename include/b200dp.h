@@ -133,7 +133,9 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     sysroot=<dir for numa_node lookups, default "/">, p2p_bytes=<default 268435456>,
  *                     busy=probe|skip|shrink (what to do on a GPU another process is using; default probe),
  *                     shrink_bytes=<prefix verified by busy=shrink, default 67108864>, ecc=1 (also fail on new
- *                     uncorrected ECC errors, one NVML query per device per pass).
+ *                     uncorrected ECC errors, one NVML query per device per pass), xid=1 (also fail a device
+ *                     for good once NVML delivers a critical Xid event for it -- application-level Xids 13, 31,
+ *                     43, 45, 68, 109 are ignored; one non-blocking nvmlEventSetWait per pass).
  * B2DP_E_NODRIVER (kfd: driver dir absent) | B2DP_E_NOGPU | B2DP_E_CUDA | B2DP_E_INVAL. */
 B2DP_API int b2dp_open(const char *backend_uri, b2dp_ctx **out);
 B2DP_API void b2dp_close(b2dp_ctx *ctx);
@@ -191,15 +193,18 @@ typedef struct b2dp_probe_result {
 #define B2DP_RES_SKIPPED_BUSY 0x1u /* busy=skip: another process owns the GPU, no pass ran, the last verdict stands */
 #define B2DP_RES_SHRUNK 0x2u       /* busy=shrink: a prefix (shrink_bytes) was verified without re-keying; no GB/s floor */
 #define B2DP_RES_ECC 0x4u          /* ecc=1: NVML reports new uncorrected ECC errors since open => Unhealthy */
+#define B2DP_RES_XID 0x8u          /* xid=1: a critical Xid event was delivered for this device since open (or the
+                                      last b2dp_probe_reset) => Unhealthy, sticky */
 
 /* Launch the probe on every GPU of the context concurrently (one worker thread + stream per
  * GPU; all launched before any is waited on) and collect one result per device. */
 B2DP_API int b2dp_probe_health(b2dp_ctx *ctx, const b2dp_probe_opts *opts, b2dp_probe_result *out, int cap, int *n);
 
 /* Test hook (fault injection): XOR `mask` into 32-bit word `word_index` of the buffer the
- * NEXT probe of `device` will read.  The reference has no equivalent. */
+ * NEXT probe of `device` will read.  word_index == UINT64_MAX instead queues a synthetic critical-Xid
+ * event numbered `mask` for `device` (seen by contexts opened with xid=1).  The reference has no equivalent. */
 B2DP_API int b2dp_probe_inject_fault(b2dp_ctx *ctx, int device, uint64_t word_index, uint32_t mask);
-/* Re-fill the probe buffers of `device` (-1 = all) with a clean pattern. */
+/* Re-fill the probe buffers of `device` (-1 = all) with a clean pattern; also clears a latched Xid. */
 B2DP_API int b2dp_probe_reset(b2dp_ctx *ctx, int device);
 /* Copy `n_words` words starting at `word_index` of the buffer the next probe will read
  * (parity tests compare it with the oracle's pattern). */

@@ -71,6 +71,11 @@ struct Nvml {
     int (*mig_mode)(void*, unsigned*, unsigned*) = nullptr;
     int (*running_procs)(void*, unsigned*, void*) = nullptr;        // nvmlDeviceGetComputeRunningProcesses_v3
     int (*ecc_total)(void*, int, int, unsigned long long*) = nullptr;  // nvmlDeviceGetTotalEccErrors
+    struct EventData { void* device; unsigned long long type, data; unsigned gi, ci; };  // nvmlEventData_t
+    int (*event_set_create)(void**) = nullptr;
+    int (*register_events)(void*, unsigned long long, void*) = nullptr;
+    int (*event_wait)(void*, EventData*, unsigned) = nullptr;          // nvmlEventSetWait_v2
+    int (*event_set_free)(void*) = nullptr;
     bool ok = false;
     void load() {
         lib = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
@@ -83,6 +88,10 @@ struct Nvml {
         mig_mode = (int (*)(void*, unsigned*, unsigned*))dlsym(lib, "nvmlDeviceGetMigMode");
         running_procs = (int (*)(void*, unsigned*, void*))dlsym(lib, "nvmlDeviceGetComputeRunningProcesses_v3");
         ecc_total = (int (*)(void*, int, int, unsigned long long*))dlsym(lib, "nvmlDeviceGetTotalEccErrors");
+        event_set_create = (int (*)(void**))dlsym(lib, "nvmlEventSetCreate");
+        register_events = (int (*)(void*, unsigned long long, void*))dlsym(lib, "nvmlDeviceRegisterEvents");
+        event_wait = (int (*)(void*, EventData*, unsigned))dlsym(lib, "nvmlEventSetWait_v2");
+        event_set_free = (int (*)(void*))dlsym(lib, "nvmlEventSetFree");
         ok = init && init() == 0;
     }
 };
@@ -108,6 +117,8 @@ struct Gpu {
     void* nvh = nullptr;                  // NVML device handle (optional)
     unsigned long long ecc_base = 0;      // uncorrected volatile ECC count when the context was opened
     bool have_ecc = false;
+    bool xid_registered = false;
+    unsigned long long xid_fault = 0;     // first critical Xid seen on this device (sticky, like a real fault)
     int last_healthy = 1;
     // worker
     std::thread th;
@@ -137,6 +148,8 @@ public:
     std::string driver_version, driver_src_version;
     std::mutex probe_mu;  // one fan-out at a time
     std::mutex bc_mu;
+    void* xid_set = nullptr;                         // NVML event set (xid=1)
+    std::deque<std::pair<int, unsigned long long>> xid_injected;  // test hook: (device, xid), guarded by probe_mu
     std::map<unsigned long long, std::array<unsigned long long, 32>> bitcounts;
     unsigned long long n_vec() const { return cfg.bytes / 16; }
 };
@@ -297,6 +310,14 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         be->gpus[i]->peer_enabled.assign(be->gpus.size(), 0);
     }
 
+    // xid=1: one NVML event set for the node, every GPU registered for critical Xid events
+    if (cfg.check_xid && be->nvml.ok && be->nvml.event_set_create && be->nvml.register_events && be->nvml.event_wait &&
+        be->nvml.event_set_create(&be->xid_set) == 0) {
+        for (auto& gp : be->gpus)
+            if (gp->nvh && be->nvml.register_events(gp->nvh, 0x8ull /*nvmlEventTypeXidCriticalError*/, be->xid_set) == 0)
+                gp->xid_registered = true;
+    }
+
     // start workers and allocate per-GPU state on them
     for (auto& gp : be->gpus) gp->th = std::thread(worker_loop, gp.get());
     std::vector<std::shared_ptr<Completion>> cs;
@@ -363,6 +384,7 @@ void cuda_backend_close(CudaBackend* be) {
         g->cv.notify_all();
         g->th.join();
     }
+    if (be->xid_set && be->nvml.event_set_free) be->nvml.event_set_free(be->xid_set);
     delete be;
 }
 
@@ -458,6 +480,31 @@ static void probe_collect(Gpu* g, ProbeJobResult* r, unsigned long long n_vec) {
         // reported exactly once, a stuck cell shows up again on the next pass
         hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
         cudaStreamSynchronize(g->stream);
+    }
+}
+
+// Xids that report an application's own fault (bad kernel, MMU fault of a user context, preemption,
+// user-stopped) rather than a broken device -- the list NVIDIA's own device plugin ignores.
+static bool xid_is_application_error(unsigned long long xid) {
+    switch (xid) { case 13: case 31: case 43: case 45: case 68: case 109: return true; default: return false; }
+}
+
+// xid=1: drain pending critical-Xid events (non-blocking) and latch them on their device.
+static void drain_xid_events(CudaBackend* be) {
+    auto latch = [&](Gpu* g, unsigned long long xid) {
+        if (!xid_is_application_error(xid) && !g->xid_fault) g->xid_fault = xid ? xid : 999;
+    };
+    while (!be->xid_injected.empty()) {
+        auto ev = be->xid_injected.front();
+        be->xid_injected.pop_front();
+        if (ev.first >= 0 && ev.first < (int)be->gpus.size()) latch(be->gpus[(size_t)ev.first].get(), ev.second);
+    }
+    if (!be->xid_set || !be->nvml.event_wait) return;
+    Nvml::EventData d{};
+    for (int guard = 0; guard < 64 && be->nvml.event_wait(be->xid_set, &d, 0) == 0; ++guard) {
+        if (d.type != 0x8ull) continue;  // nvmlEventTypeXidCriticalError
+        for (auto& g : be->gpus)
+            if (g->nvh == d.device) latch(g.get(), d.data);
     }
 }
 
@@ -602,6 +649,15 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         }
         be->gpus[i]->last_healthy = o.healthy;
     }
+    if (be->cfg.check_xid) {  // opt-in: a critical Xid since open fails the device whatever the pass said
+        drain_xid_events(be);
+        for (size_t i = 0; i < n; ++i)
+            if (be->gpus[i]->xid_fault) {
+                out[i].flags |= B2DP_RES_XID;
+                out[i].healthy = 0;
+                be->gpus[i]->last_healthy = 0;
+            }
+    }
     return B2DP_OK;
 }
 
@@ -614,6 +670,10 @@ int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask,
     std::lock_guard<std::mutex> pl(be->probe_mu);
     Gpu* g = gpu_at(be, device, err);
     if (!g) return B2DP_E_INVAL;
+    if (word == ~0ull) {  // synthetic critical-Xid event `mask`, handled like one delivered by NVML (xid=1)
+        if (be->cfg.check_xid) be->xid_injected.emplace_back(device, (unsigned long long)mask);
+        return B2DP_OK;
+    }
     if (word >= be->n_vec() * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
     cudaError_t ce = cudaSuccess;
     run_sync(g, [&] {
@@ -630,6 +690,7 @@ int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
     for (int i = 0; i < (int)be->gpus.size(); ++i) {
         if (device >= 0 && device != i) continue;
         Gpu* g = be->gpus[i].get();
+        g->xid_fault = 0;  // operator acknowledgement: a latched Xid is cleared together with the buffers
         cudaError_t ce = cudaSuccess;
         run_sync(g, [&] {
             hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);

@@ -98,6 +98,7 @@ struct CudaConfig {
     int busy_policy = 0;                 // 0 probe always, 1 skip busy GPUs, 2 shrink on busy GPUs
     uint64_t shrink_bytes = 64ull << 20;
     bool check_ecc = false;
+    bool check_xid = false;
 };
 int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err);
 void cuda_backend_close(CudaBackend*);

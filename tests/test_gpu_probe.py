@@ -311,6 +311,36 @@ def test_ecc_option_is_harmless(P):
         assert r.healthy and not (r.flags & P._native.RES_ECC)
 
 
+def test_xid_option_latches_critical_events_and_ignores_application_xids(P):
+    """`xid=1`: the NVML critical-Xid event set is drained once per pass.  No hardware fault can be
+    provoked here, so synthetic events go through the same handler (word_index = UINT64_MAX): an
+    application-level Xid (31 = MMU fault of a user context) changes nothing; a device-level one (79 =
+    fallen off the bus) fails the device on every later pass although the HBM pass itself is clean,
+    until probe_reset acknowledges it.  Without xid=1 the events are not looked at."""
+    UINT64_MAX = (1 << 64) - 1
+    with _open(P, 16 * MiB, ",xid=1") as ctx:
+        (r,) = ctx.probe_health(min_gbs=1e-3)
+        assert r.healthy and not (r.flags & P._native.RES_XID)     # live event set: nothing pending
+        ctx.probe_inject_fault(0, UINT64_MAX, 31)
+        (r,) = ctx.probe_health(min_gbs=1e-3)
+        assert r.healthy and r.flags == 0
+        ctx.probe_inject_fault(0, UINT64_MAX, 79)
+        for _ in range(2):
+            (r,) = ctx.probe_health(min_gbs=1e-3)
+            assert not r.healthy and r.flags & P._native.RES_XID
+            assert r.mismatches == 0 and r.checksum == r.expected_checksum and r.err == 0
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT, min_gbs=1e-3)
+        assert st.n_unhealthy == 1
+        assert P.v1beta1.ListAndWatchResponse.FromString(wire).devices[0].health == "Unhealthy"
+        ctx.probe_reset(0)
+        (r,) = ctx.probe_health(min_gbs=1e-3)
+        assert r.healthy and r.flags == 0
+    with _open(P, 16 * MiB) as ctx:
+        ctx.probe_inject_fault(0, UINT64_MAX, 79)
+        (r,) = ctx.probe_health(min_gbs=1e-3)
+        assert r.healthy and r.flags == 0
+
+
 def test_word_index_wraps_past_16_gib(P):
     """Maximum sizes: a buffer larger than 2^32 words (16 GiB) makes the 32-bit word index of the
     pattern wrap.  Size-independent property: one full period of (uint32(i) * K) ^ seed visits every
