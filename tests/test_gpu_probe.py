@@ -341,6 +341,44 @@ def test_xid_option_latches_critical_events_and_ignores_application_xids(P):
         assert r.healthy and r.flags == 0
 
 
+@pytest.mark.parametrize("via_workers", [False, True])
+def test_deadline_expiry_reports_unhealthy_and_recovers(P, via_workers):
+    """health.go:37 gives the exporter RPC a deadline; here a pass that misses `timeout_ms` is reported
+    Unhealthy with B2DP_E_TIMEOUT without blocking the caller, the late pass is collected by the GPU's
+    worker, and the next heartbeat carries on from the state that pass left (seed advanced once)."""
+    import time
+    import torch
+    nbytes = 8 << 30                                   # ~2.7 ms per pass: a 1 ms deadline always expires
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 2 * nbytes + (2 << 30):
+        pytest.skip("not enough free HBM")
+    n_check = 1 << 20
+    with _open(P, nbytes) as ctx:
+        seed = oprobe.initial_seed(0)
+        t0 = time.perf_counter()
+        (r,) = ctx.probe_health(timeout_ms=1, via_workers=via_workers, min_gbs=1e-3)
+        waited = time.perf_counter() - t0
+        assert r.err == P._native.E_TIMEOUT and not r.healthy
+        assert waited < 0.5                            # the call returned at the deadline, not at completion
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT, timeout_ms=1, min_gbs=1e-3)
+        assert st.n_unhealthy == 1                     # still in flight or timed out again: Unhealthy either way
+        time.sleep(0.2)                                # the worker collects the late passes
+        for _ in range(20):
+            (r,) = ctx.probe_health(min_gbs=1e-3, via_workers=via_workers)
+            if r.err == 0:
+                break
+            time.sleep(0.05)
+        assert r.err == 0 and r.healthy and r.mismatches == 0 and r.checksum == r.expected_checksum
+        # the timed-out passes did run to completion: the seed moved on once per completed pass
+        steps = 0
+        s = seed
+        while s != r.seed and steps < 4:
+            s = oprobe.next_seed(s)
+            steps += 1
+        assert 1 <= steps <= 2 and s == r.seed
+        assert np.array_equal(ctx.probe_peek(0, 0, n_check), oprobe.pattern(n_check, oprobe.next_seed(r.seed)))
+
+
 def test_word_index_wraps_past_16_gib(P):
     """Maximum sizes: a buffer larger than 2^32 words (16 GiB) makes the 32-bit word index of the
     pattern wrap.  Size-independent property: one full period of (uint32(i) * K) ^ seed visits every
