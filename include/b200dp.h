@@ -276,7 +276,9 @@ B2DP_API int b2dp_watch_beat(b2dp_watch *w);
 B2DP_API void b2dp_watch_stop(b2dp_watch *w);
 
 /* plugin.go:356-393 Allocate for one container request: "/dev/kfd" first, then the two
- * /dev/dri paths of every known id (card, then renderD); unknown ids add nothing.
+ * /dev/dri paths of every known id (card, then renderD); unknown ids add nothing.  "Known" = the device
+ * table of this context's last INITIAL ListAndWatch (the reference reads p.AMDGPUs, plugin.go:231,375);
+ * a context that has not streamed yet enumerates instead (the reference would know no id at all).
  * cuda backend: /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools, then /dev/nvidia<minor>. */
 B2DP_API int b2dp_device_specs(b2dp_ctx *ctx, const char *const *ids, int n_ids, b2dp_devspec *out, int cap, int *n);
 /* Same, serialized as v1beta1.ContainerAllocateResponse (api.proto: devices=3).  The cuda backend also sets

@@ -504,9 +504,18 @@ extern "C" void b2dp_watch_stop(b2dp_watch* w) {
 
 // ---- Allocate ----------------------------------------------------------------------------
 static int device_specs(b2dp_ctx* c, const char* const* ids, int n_ids, std::vector<b2dp_devspec>& specs) {
+    // plugin.go:375 reads p.AMDGPUs, the table built when the ListAndWatch stream started (plugin.go:231):
+    // use that snapshot; only a context that never streamed enumerates here
     std::vector<Device> devs;
-    int rc = enumerate_ctx(c, devs);
-    if (rc != B2DP_OK) return rc;
+    bool have = false;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (c->have_stream_devs) { devs = c->stream_devs; have = true; }
+    }
+    if (!have) {
+        int rc = enumerate_ctx(c, devs);
+        if (rc != B2DP_OK) return rc;
+    }
     auto push = [&](const std::string& p) {
         b2dp_devspec s{};
         copy_str(s.host_path, sizeof s.host_path, p);

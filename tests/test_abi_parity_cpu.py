@@ -316,6 +316,28 @@ def test_plugin_on_kfd_backend(P, kfd, tmp_path):
         assert ctx.device_specs([ids[0]]) == oplug.allocate_device_specs(gpus, [ids[0]])
 
 
+def test_allocate_reads_the_stream_snapshot(P, kfd, tmp_path):
+    """plugin.go:375 indexes p.AMDGPUs -- the table built when the ListAndWatch stream started
+    (plugin.go:231) -- not the live sysfs: a device that disappears afterwards is still allocatable
+    with its old paths until the stream restarts, and heartbeats keep sending the old list."""
+    import shutil
+    root = fake_sysfs.build(str(tmp_path / "r"), topo_dir(kfd, "mi210"))
+    gpus = oamd.GetAMDGPUs(root)
+    ids = sorted(gpus)
+    gone = ids[1]
+    V = P.v1beta1
+    with P.Context("kfd:" + root) as ctx:
+        ctx.list_and_watch("gpu", P._native.LW_INITIAL)
+        shutil.rmtree(os.path.join(root, "sys/module/amdgpu/drivers/pci:amdgpu", gone))
+        assert gone not in ctx.enumerate() and gone not in oamd.GetAMDGPUs(root)
+        assert ctx.device_specs([gone]) == oplug.allocate_device_specs(gpus, [gone])          # snapshot, like p.AMDGPUs
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT | P._native.LW_NO_PROBE)
+        assert [d.ID for d in V.ListAndWatchResponse.FromString(wire).devices] == ids
+        ctx.list_and_watch("gpu", P._native.LW_INITIAL)                                       # stream restart
+        now = oamd.GetAMDGPUs(root)
+        assert ctx.device_specs([gone]) == oplug.allocate_device_specs(now, [gone]) == [("/dev/kfd", "/dev/kfd", "rw")]
+
+
 def test_list_and_watch_heterogeneous(P, kfd, tmp_path):
     root = fake_sysfs.build(str(tmp_path / "r"), topo_dir(kfd, "mi308"), compute="cpx", memory="nps1",
                             hetero_second=("spx", "nps1"))
