@@ -386,7 +386,7 @@ def main():
                 "ms_encode": round(enc_ms / args.steps, 5), "response_bytes": len(wire),
                 "stream_start_ms": round(stream_start_ms, 4),
                 "heartbeat_to_kubelet_grpc_ms": None if grpc_ms is None or grpc_ms < 0 else round(grpc_ms, 4),
-                "note": "no bulk host buffers on this path: kernel arguments in, 48-byte result block (pinned mapped) + serialized response out"},
+                "note": "no bulk host buffers on this path: kernel arguments in, 48-byte result block (pinned mapped) + serialized response out; the value leg brackets every kernel with CUDA events (the roofline's clock), the kubelet-facing call completes on the published result block alone"},
         "gpu_launches": args.steps * n,
         "unhealthy_verdicts": int(unhealthy),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",

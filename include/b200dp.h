@@ -173,7 +173,11 @@ typedef struct b2dp_probe_opts {
 #define B2DP_PROBE_VARIANT_MASK 0xfu
 #define B2DP_PROBE_VIA_WORKERS 0x10u     /* launch + wait on each GPU's own worker thread (full isolation from a
                                             wedged driver call) instead of the default low-latency path where the
-                                            calling thread enqueues on every stream and polls the events */
+                                            calling thread enqueues on every stream and polls the pinned result
+                                            blocks */
+#define B2DP_PROBE_EVENT_TIMING 0x20u    /* also bracket each kernel with CUDA events and report ms_event (what the
+                                            roofline is measured with; ~1.5 us more enqueue work per GPU).  Without
+                                            it ms_event = 0 and gbs comes from the in-kernel %globaltimer span */
 
 typedef struct b2dp_probe_result {
     int32_t device;             /* index into b2dp_enumerate() order */
@@ -185,9 +189,9 @@ typedef struct b2dp_probe_result {
     uint64_t mismatches;        /* words != pattern */
     uint64_t first_bad_word;    /* min bad word index, UINT64_MAX if none */
     uint64_t bytes;             /* algorithmic bytes moved: 2 * S */
-    float ms_event;             /* CUDA-event time of the probe kernel */
-    float ms_device;            /* %globaltimer span inside the kernel */
-    float gbs;                  /* bytes / ms_event */
+    float ms_event;             /* CUDA-event time of the probe kernel (B2DP_PROBE_EVENT_TIMING), else 0 */
+    float ms_device;            /* %globaltimer span inside the kernel: first CTA start .. result published */
+    float gbs;                  /* bytes / ms_event when event-timed, else bytes / ms_device */
     uint32_t flags;             /* B2DP_RES_* */
 } b2dp_probe_result;
 #define B2DP_RES_SKIPPED_BUSY 0x1u /* busy=skip: another process owns the GPU, no pass ran, the last verdict stands */

@@ -111,8 +111,13 @@ class Context:
         N.check(N.lib.b2dp_node_health(self._h, C.byref(v)), self._h)
         return bool(v.value)
 
-    def probe_health(self, timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0, via_workers=False) -> List[ProbeResult]:
-        opts = N.ProbeOpts(timeout_ms, variant | (N.PROBE_VIA_WORKERS if via_workers else 0), min_gbs, 0)
+    def probe_health(self, timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0, via_workers=False,
+                     timed=True) -> List[ProbeResult]:
+        """One fan-out pass.  timed=True brackets each kernel with CUDA events (ms_event, what the roofline
+        is measured with); timed=False is the kubelet-facing configuration (completion by the published
+        result block alone, GB/s from the in-kernel timer)."""
+        opts = N.ProbeOpts(timeout_ms, variant | (N.PROBE_VIA_WORKERS if via_workers else 0)
+                           | (N.PROBE_EVENT_TIMING if timed else 0), min_gbs, 0)
         rc, arr, n = N.grow_call(lambda cap: (N.ProbeResult * cap)(),
                                  lambda a, cap, pn: N.lib.b2dp_probe_health(self._h, C.byref(opts), a, cap, pn))
         N.check(rc, self._h)
@@ -134,11 +139,11 @@ class Context:
 
     # ---- ListAndWatch --------------------------------------------------------------------
     def list_and_watch(self, resource: str = "gpu", flags: int = N.LW_INITIAL, external: Optional[Dict[str, bool]] = None,
-                       timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0):
+                       timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0, timed=False):
         """One ListAndWatch send: (serialized ListAndWatchResponse bytes, CycleStats)."""
         opts = N.CycleOpts()
         opts.flags = flags
-        opts.probe = N.ProbeOpts(timeout_ms, variant, min_gbs, 0)
+        opts.probe = N.ProbeOpts(timeout_ms, variant | (N.PROBE_EVENT_TIMING if timed else 0), min_gbs, 0)
         keep = None
         if external is not None:
             opts.flags |= N.LW_EXTERNAL_SOURCE

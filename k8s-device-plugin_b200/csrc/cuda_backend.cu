@@ -432,6 +432,7 @@ struct ProbeJobResult {
     bool seq_ok = false;
     unsigned long long n_vec = 0;   // vectors this pass covers (shrunk on a busy GPU)
     bool advance = true;            // false: verify-only prefix pass, buffers/seed stay as they are
+    bool timed = false;             // bracket the kernel with CUDA events (B2DP_PROBE_EVENT_TIMING)
 };
 
 static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uint32_t seed, uint32_t delta,
@@ -452,16 +453,26 @@ static void probe_issue(Gpu* g, ProbeJobResult* r, unsigned long long n_vec_full
     r->n_vec = n_vec;
     r->seed = seed;
     r->seq = ++g->seq;
-    cudaEventRecord(g->e0, g->stream);
+    if (r->timed) cudaEventRecord(g->e0, g->stream);
     launch_probe(g, n_vec, variant, seed, r->advance ? seed ^ next : 0u, g->buf[g->cur], g->buf[g->next()], r->seq);
     r->ce = cudaGetLastError();
-    cudaEventRecord(g->e1, g->stream);
+    if (r->timed) cudaEventRecord(g->e1, g->stream);
 }
 
-// After e1 completed: read the published result, advance the seed / ping-pong state.
+// The last CTA publishes the result block and, after a system-scope fence, the launch's sequence
+// number into pinned host memory (hbm_probe.cuh finish()): seeing the number means every CTA's
+// stores and the whole block are done -- completion without a driver call.
+static inline bool probe_published(const Gpu* g, const ProbeJobResult* r) {
+    return *(volatile const unsigned long long*)&g->out_h->seq == r->seq;
+}
+
+// After the pass completed: read the published result, advance the seed / ping-pong state.
 static void probe_collect(Gpu* g, ProbeJobResult* r, unsigned long long n_vec) {
     cudaError_t e = r->ce;
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&r->ms, g->e0, g->e1);
+    if (e == cudaSuccess && r->timed) {
+        e = cudaEventSynchronize(g->e1);  // the result is already published; the event follows within ~1 us
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&r->ms, g->e0, g->e1);
+    }
     r->ce = e;
     if (e != cudaSuccess) return;
     memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // published before the event fired
@@ -516,6 +527,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     if (rc != B2DP_OK) return rc;
     const uint32_t variant = opts ? (opts->flags & B2DP_PROBE_VARIANT_MASK) : 0;
     const bool via_workers = opts && (opts->flags & B2DP_PROBE_VIA_WORKERS);
+    const bool timed = opts && (opts->flags & B2DP_PROBE_EVENT_TIMING);
     const uint32_t timeout_ms = opts && opts->timeout_ms ? opts->timeout_ms : 5000;  // health.go:37
     const float min_gbs = opts && opts->min_gbs > 0 ? opts->min_gbs : be->cfg.min_gbs;
     const size_t n = be->gpus.size();
@@ -523,7 +535,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     std::vector<std::shared_ptr<Completion>> cs(n);
     std::vector<char> state(n, 0);  // 0 pending, 1 done, 2 timed out / busy
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
-    for (size_t i = 0; i < n; ++i) res[i] = std::make_shared<ProbeJobResult>();
+    for (size_t i = 0; i < n; ++i) { res[i] = std::make_shared<ProbeJobResult>(); res[i]->timed = timed; }
     // busy policy (tenant workloads): a 2 GiB-traffic probe steals bandwidth from a pod that owns the
     // GPU; `busy=skip` keeps the last verdict, `busy=shrink` verifies a small prefix without re-keying
     std::vector<uint32_t> rflags(n, 0);
@@ -552,10 +564,12 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             auto r = res[i];
             if (state[i] != 0) continue;
             if (g->inflight.load()) { state[i] = 2; continue; }
+            g->inflight.store(true);  // until collected: a pass that misses the deadline still owns seed/ring state
             cs[i] = post(g, [g, r, n_vec, variant] {
                 probe_issue(g, r.get(), n_vec, variant);
-                if (r->ce == cudaSuccess) r->ce = cudaEventSynchronize(g->e1);
+                if (r->ce == cudaSuccess) r->ce = cudaStreamSynchronize(g->stream);
                 probe_collect(g, r.get(), n_vec);
+                g->inflight.store(false);
             });
         }
         for (size_t i = 0; i < n; ++i)
@@ -581,15 +595,20 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             for (size_t i = 0; i < n; ++i) {
                 if (state[i] != 0) continue;
                 Gpu* g = be->gpus[i].get();
-                cudaError_t q = res[i]->ce != cudaSuccess ? res[i]->ce : cudaEventQuery(g->e1);
-                if (q == cudaErrorNotReady) continue;
-                if (q != cudaSuccess) res[i]->ce = q;
+                if (res[i]->ce == cudaSuccess && !probe_published(g, res[i].get())) {
+                    // not there yet; now and then ask the driver too, so that a faulted kernel (which
+                    // never publishes) is reported at once instead of at the deadline
+                    if ((spins & 0x3ff) != 0x3ff) continue;
+                    const cudaError_t q = cudaStreamQuery(g->stream);
+                    if (q == cudaErrorNotReady) continue;
+                    if (q != cudaSuccess) res[i]->ce = q;
+                }
                 cudaSetDevice(g->ordinal);
                 probe_collect(g, res[i].get(), n_vec);
                 state[i] = 1;
                 --pending;
             }
-            if (pending && (++spins & 0xff) == 0 && std::chrono::steady_clock::now() > deadline) break;
+            if (pending && (++spins & 0x3ff) == 0 && std::chrono::steady_clock::now() > deadline) break;
         }
         for (size_t i = 0; i < n; ++i) {
             if (state[i] != 0) continue;
@@ -598,7 +617,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             auto r = res[i];
             g->inflight.store(true);
             post(g, [g, r, n_vec] {
-                if (r->ce == cudaSuccess) r->ce = cudaEventSynchronize(g->e1);
+                if (r->ce == cudaSuccess) r->ce = cudaStreamSynchronize(g->stream);
                 probe_collect(g, r.get(), n_vec);
                 g->inflight.store(false);
             });
@@ -633,9 +652,10 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.checksum = r.out.checksum;
         o.mismatches = r.out.mismatches;
         o.first_bad_word = r.out.first_bad;
-        o.ms_event = r.ms;
+        o.ms_event = r.ms;  // 0 unless B2DP_PROBE_EVENT_TIMING
         o.ms_device = (float)((double)(r.out.t_end_ns - r.out.t_start_ns) * 1e-6);
-        o.gbs = r.ms > 0 ? (float)((double)o.bytes / (double)r.ms * 1e-6) : 0.f;
+        const float ms_for_rate = r.timed ? r.ms : o.ms_device;
+        o.gbs = ms_for_rate > 0 ? (float)((double)o.bytes / (double)ms_for_rate * 1e-6) : 0.f;
         // verdict (oracle/probe.py probe_healthy)
         // a shrunk pass shares the GPU with a tenant: integrity only, no bandwidth floor
         const bool fast_enough = (o.flags & B2DP_RES_SHRUNK) ? true : o.gbs >= min_gbs;
@@ -730,6 +750,9 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
     const unsigned long long n_vec = bytes / 16;
     const int iters = opts && opts->iters ? (int)opts->iters : 2;
     for (int i = 0; i < n * n; ++i) { gbs[i] = 0; link_type[i] = 0; mism[i] = 0; }
+    // a probe pass that missed its deadline still owns its GPU's seed/ring state: let the workers drain
+    for (auto& g : be->gpus)
+        if (g->inflight.load()) run_sync(g.get(), [] {});
     std::array<unsigned long long, 32> bc;
     int rc = get_bitcounts(be, n_vec * 4, bc, err);
     if (rc != B2DP_OK) return rc;

@@ -69,7 +69,9 @@ int main(int argc, char** argv) {
             const double t0 = now_ms();
             if (cmd == "probe") {
                 int m = 0;
-                if ((rc = b2dp_probe_health(ctx, nullptr, res.data(), (int)res.size(), &m)) != B2DP_OK) return die(ctx, "b2dp_probe_health", rc);
+                b2dp_probe_opts po{};
+                po.flags = B2DP_PROBE_EVENT_TIMING;   // kernel_ms_median below is the CUDA-event time
+                if ((rc = b2dp_probe_health(ctx, &po, res.data(), (int)res.size(), &m)) != B2DP_OK) return die(ctx, "b2dp_probe_health", rc);
                 if (i >= 0) { bytes = 0; for (int k = 0; k < m; ++k) { bytes += (double)res[k].bytes; kern.push_back(res[k].ms_event); if (!res[k].healthy) return die(ctx, "unhealthy device", res[k].err); } }
             } else {
                 if ((rc = b2dp_list_and_watch(ctx, "gpu", &co, buf.data(), buf.size(), &len, &st)) != B2DP_OK) return die(ctx, "b2dp_list_and_watch", rc);
