@@ -475,7 +475,8 @@ static void probe_collect(Gpu* g, ProbeJobResult* r, unsigned long long n_vec) {
     }
     r->ce = e;
     if (e != cudaSuccess) return;
-    memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // published before the event fired
+    std::atomic_thread_fence(std::memory_order_acquire);       // the sequence number was read first (probe_published)
+    memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // the block is complete once its sequence number shows
     r->seq_ok = r->out.seq == r->seq;
     if (!r->advance) {
         if (r->out.mismatches != 0 || !r->seq_ok) {  // repair the source buffer in place
