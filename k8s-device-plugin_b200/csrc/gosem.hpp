@@ -36,6 +36,7 @@ inline bool read_file(const std::string& path, std::string& out) {
         if (r < 0) { ::close(fd); return false; }
         if (r == 0) break;
         out.append(buf, (size_t)r);
+        if ((size_t)r < sizeof buf) break;  // short read of a regular/sysfs file = EOF: saves the extra read() per file
     }
     ::close(fd);
     return true;

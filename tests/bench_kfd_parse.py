@@ -99,7 +99,7 @@ def main():
         rows.append(row)
         ctx.close()
     out = {"host_cores": os.cpu_count(), "threads_used": 1, "rows": rows,
-           "note": "port = C restatement of the Go walk (no Go toolchain in the image); all single-threaded"}
+           "note": "port = C restatement of the Go walk (no Go toolchain in the image), single-threaded like the reference's single goroutine; the product is single-threaded too except pair-weight init, which parses a tree of >= 512 link files on up to 8 threads (records applied in the reference's order)"}
     s = json.dumps(out, indent=1)
     print(s)
     if args.out:
