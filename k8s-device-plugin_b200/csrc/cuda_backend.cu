@@ -76,11 +76,17 @@ struct Nvml {
     int (*register_events)(void*, unsigned long long, void*) = nullptr;
     int (*event_wait)(void*, EventData*, unsigned) = nullptr;          // nvmlEventSetWait_v2
     int (*event_set_free)(void*) = nullptr;
+    int (*shutdown)() = nullptr;
     bool ok = false;
+    ~Nvml() {
+        if (ok && shutdown) shutdown();  // nvmlInit/nvmlShutdown are reference counted
+        if (lib) dlclose(lib);
+    }
     void load() {
         lib = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
         if (!lib) return;
         init = (int (*)())dlsym(lib, "nvmlInit_v2");
+        shutdown = (int (*)())dlsym(lib, "nvmlShutdown");
         driver_version = (int (*)(char*, unsigned))dlsym(lib, "nvmlSystemGetDriverVersion");
         handle_by_bus_id = (int (*)(const char*, void**))dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2");
         minor_number = (int (*)(void*, unsigned*))dlsym(lib, "nvmlDeviceGetMinorNumber");
@@ -239,6 +245,9 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
     std::vector<int> ords = cfg.devices;
     if (ords.empty()) for (int i = 0; i < count; ++i) ords.push_back(i);
     for (int o : ords) if (o < 0 || o >= count) { err = "device ordinal out of range"; return B2DP_E_INVAL; }
+    for (size_t a = 0; a < ords.size(); ++a)
+        for (size_t b = a + 1; b < ords.size(); ++b)
+            if (ords[a] == ords[b]) { err = "device ordinal listed twice"; return B2DP_E_INVAL; }
 
     if (be->nvml.ok && be->nvml.driver_version) {
         char buf[96] = {0};

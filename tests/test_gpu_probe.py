@@ -300,7 +300,7 @@ def test_scrub_ring_rotates_through_all_slots(P):
                 assert np.array_equal(ctx.probe_peek(0, 0, n_words), dst)
             else:
                 assert np.array_equal(ctx.probe_peek(0, 0, n_words), oprobe.pattern(n_words, seed))
-    for bad_uri in ("cuda:devices=0,slots=1", "cuda:devices=0,slots=99999"):
+    for bad_uri in ("cuda:devices=0,slots=1", "cuda:devices=0,slots=99999", "cuda:devices=0+0", "cuda:devices=999"):
         with pytest.raises(P._native.B2dpError):
             P.Context(bad_uri)
 
