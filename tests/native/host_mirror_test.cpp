@@ -264,7 +264,47 @@ static void TestPluginFlowOnSysroot() {
     CHECK(labels.count("amd.com/gpu.cu-count") && labels["amd.com/gpu.compute-memory-partition"] == "cpx_nps4");
 }
 
+// ---- the same plugin flow on real B200s (`host_mirror_test --cuda <uri>`, run by the -m gpu suite) -------------------
+static std::string g_uri;
+static void TestPluginFlowOnCuda() {
+    auto oc = Context::Open(g_uri);
+    CHECK(!oc.second);
+    if (oc.second) { fprintf(stderr, "open: %s\n", oc.second.what().c_str()); return; }
+    Ctx ctx = oc.first;
+    auto gpus = amdgpu::GetAMDGPUs(ctx);
+    CHECK(!gpus.empty() && amdgpu::IsHomogeneous(ctx));
+    plugin::AMDGPULister lister(ctx);
+    auto p = lister.NewPlugin("gpu");
+    CHECK(!p->Start());
+    CHECK(p->allocatorInitError == (gpus.size() < 2));  // one GPU: no pair weights, kubelet default allocation
+    std::vector<std::string> sent;
+    int ticks = 3;
+    Error e = p->ListAndWatch([&](const std::string& wire) { sent.push_back(wire); }, [&] { return ticks-- > 0; });
+    CHECK(!e && sent.size() == 4 && sent[0] == sent[3]);                        // every heartbeat: all Healthy again
+    CHECK(p->last_stats.n_devices == (int)gpus.size() && p->last_stats.n_unhealthy == 0 && p->last_stats.node_healthy);
+    CHECK(p->last_stats.probe_gbs_min > 1000.f && p->last_stats.probe_bytes > 0);  // the HBM pass ran on every GPU
+    std::vector<std::string> ids;
+    for (auto& kv : gpus) ids.push_back(kv.first);
+    auto al = p->Allocate({{ids[0]}});
+    CHECK(!al.second && al.first[0].Devices.size() == 4 && al.first[0].Devices[0].HostPath == "/dev/nvidiactl");
+    CHECK(al.first[0].Devices[3].HostPath == "/dev/nvidia" + std::to_string(gpus[ids[0]].card));
+    if (gpus.size() >= 2) {
+        auto pa = p->GetPreferredAllocation({{ids, {}, 2}});
+        CHECK(!pa.second && pa.first[0].size() == 2);
+    }
+    auto labels = labeller::generateLabels(ctx, {"cu-count", "product-name"});
+    CHECK(labels["amd.com/gpu.cu-count"] == "148");
+    printf("cuda flow: %zu GPUs, min %.0f GB/s per GPU inside the heartbeat, cycle %.3f ms\n", gpus.size(),
+           p->last_stats.probe_gbs_min, p->last_stats.ms_total);
+}
+
 int main(int argc, char** argv) {
+    if (argc == 3 && std::string(argv[1]) == "--cuda") {
+        g_uri = argv[2];
+        RUN(TestPluginFlowOnCuda);
+        printf("%s: %d checks, %d failed\n", g_failed ? "FAIL" : "PASS", g_checks, g_failed);
+        return g_failed ? 1 : 0;
+    }
     if (argc < 2) { fprintf(stderr, "usage: host_mirror_test <fixtures_dir> [<cpx sysroot>]\n"); return 2; }
     testdata = argv[1];
     RUN(TestParseTopologyProperties);

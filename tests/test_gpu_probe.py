@@ -425,3 +425,30 @@ def test_native_watch_loop_on_cuda(P):
             healths.append(P.v1beta1.ListAndWatchResponse.FromString(wire).devices[0].health)
         w.stop()
         assert healths.count("Unhealthy") == 1 and healths[0] == "Healthy" and healths[-1] == "Healthy", healths
+
+
+def test_compiled_hosts_on_the_gpu(tmp_path):
+    """The two compiled hosts over the C ABI, on real hardware: the C++ mirror of the reference's plugin
+    package (include/b200dp_host.hpp; Start / ListAndWatch with the HBM pass in every heartbeat / Allocate /
+    GetPreferredAllocation / labels) and tools/b200dp_cli's kubelet-facing cycle loop."""
+    import json
+    import shutil
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    libdir = os.path.join(root, "k8s-device-plugin_b200")
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "host_mirror_test")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(here, "native", "host_mirror_test.cpp"), "-o", exe,
+                        "-L", libdir, "-lb200dp", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "--cuda", "cuda:bytes=%d,p2p_bytes=%d" % (256 * MiB, 64 * MiB)], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "PASS" in r.stdout and ", 0 failed" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    cli = os.path.join(root, "tools", "b200dp_cli")
+    if os.path.exists(cli):
+        r = subprocess.run([cli, "cuda:devices=0", "cycle", "50"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["n_devices"] == 1 and d["aggregate_gbs"] > 4000 and d["response_bytes"] > 0
