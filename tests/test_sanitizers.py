@@ -99,3 +99,25 @@ def test_tsan_shared_context_many_threads(bins, trees, which):
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-6000:])
     assert "threads ok" in r.stdout and " 0 mismatching passes, 0 failures" in r.stdout
     assert "ThreadSanitizer" not in r.stderr
+
+
+@pytest.mark.parametrize("san", ["address,undefined", "thread"])
+def test_native_daemon_under_sanitizers(san, tmp_path):
+    """b200dp_plugind (csrc/host: HTTP/2 + HPACK + gRPC, the watch threads, the signal loop) rebuilt under
+    ASan+UBSan / TSan and put through tests/test_native_plugind.py again: grpcio as the kubelet on both
+    sockets, concurrent streams, cancellation, kubelet restart, SIGUSR1, SIGTERM.  A sanitizer report makes
+    the daemon exit non-zero, which those tests check."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "plugind_san")
+    srcs = SOURCES[:-1] + [os.path.join(CSRC, "host", "plugind.cpp")]
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=" + san] + srcs +
+                       ["-o", exe, "-lpthread", "-ldl"], capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("sanitizer runtimes not installed")
+    assert r.returncode == 0, r.stderr[-4000:]
+    env = _env()
+    env["B200DP_PLUGIND"] = exe
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_native_plugind.py"), "-x", "-q",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-4000:], r.stderr[-2000:])
