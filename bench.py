@@ -360,6 +360,17 @@ def main():
         print("grpc leg skipped: %r" % (e,), file=sys.stderr)
         grpc_ms = max_over_ranks(-1.0)
 
+    # ---- the same, with the native daemon (b200dp_plugind: C++ gRPC host, own process, own probe ring on this
+    # GPU): SIGUSR1 "heartbeat now" -> probe -> ListAndWatchResponse received by a grpcio client; rank 0 only --
+    native_ms = None
+    if rank == 0:
+        try:
+            dp = importlib.import_module(PKG + ".daemon_probe")
+            native_ms = dp.heartbeat_latency_ms("cuda:devices=%d,bytes=%d" % (local_rank, S_BYTES), iters=100)
+        except Exception as e:      # noqa: BLE001
+            print("native daemon leg skipped: %r" % (e,), file=sys.stderr)
+    barrier()
+
     clocks = sampler.stop(windows) if sampler else None
     if rank != 0:
         ctx.close()
@@ -386,6 +397,7 @@ def main():
                 "ms_encode": round(enc_ms / args.steps, 5), "response_bytes": len(wire),
                 "stream_start_ms": round(stream_start_ms, 4),
                 "heartbeat_to_kubelet_grpc_ms": None if grpc_ms is None or grpc_ms < 0 else round(grpc_ms, 4),
+                "heartbeat_to_kubelet_native_daemon_ms": native_ms,
                 "note": "no bulk host buffers on this path: kernel arguments in, 48-byte result block (pinned mapped) + serialized response out; the value leg brackets every kernel with CUDA events (the roofline's clock), the kubelet-facing call completes on the published result block alone"},
         "gpu_launches": args.steps * n,
         "unhealthy_verdicts": int(unhealthy),

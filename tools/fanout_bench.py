@@ -117,6 +117,16 @@ def run(pkg, n_gpus, steps, warmup, p2p=True, grpc_leg=True):
         except Exception as e:      # noqa: BLE001
             out["grpc_error"] = repr(e)
     ctx.close()
+    if grpc_leg:
+        # the native daemon (C++ gRPC host in its own process) over the same GPUs: SIGUSR1 -> probe fan-out ->
+        # response received by a grpcio client playing the kubelet
+        try:
+            dp = importlib.import_module("k8s-device-plugin_b200.daemon_probe")
+            r = dp.heartbeat_latency_ms(uri, iters=steps)
+            out["native_daemon_heartbeat_to_kubelet_ms_median"] = r["median_ms"]
+            out["native_daemon_heartbeat_to_kubelet_ms_p99"] = r["p99_ms"]
+        except Exception as e:      # noqa: BLE001
+            out["native_daemon_error"] = repr(e)
     return out
 
 
@@ -138,7 +148,8 @@ def main():
             counts.append(total)
         res = [run(pkg, c, args.steps, args.warmup, p2p=(not args.no_p2p and c == total)) for c in counts]
         summary = [{k: r.get(k) for k in ("n_gpus", "cycle_ms_median", "cycle_ms_p99", "per_gpu_frac_of_peak",
-                                           "aggregate_gbs_in_cycle", "grpc_heartbeat_to_kubelet_ms_median")} for r in res]
+                                           "aggregate_gbs_in_cycle", "grpc_heartbeat_to_kubelet_ms_median",
+                                           "native_daemon_heartbeat_to_kubelet_ms_median")} for r in res]
         out = {"summary": summary, "runs": res}
     else:
         out = run(pkg, args.gpus, args.steps, args.warmup, p2p=not args.no_p2p)
