@@ -31,3 +31,16 @@ def test_reference_unit_tests_through_the_cpp_host_mirror(kfd, tmp_path):
                  "TestCountGPUDevFromTopology", "TestPairWeightCalculation", "TestGroupPartitionsByDevId",
                  "TestGetSubsetsMethod", "TestBestPolicyAllocator", "TestRemoveOldNodeLabels", "TestPluginFlowOnSysroot"):
         assert "ok   " + name in r.stdout
+
+
+def test_hpack_rfc7541_vectors_and_grpc_framing(tmp_path):
+    """csrc/host/h2grpc.hpp against the worked examples of RFC 7541 Appendix C (integers C.1, literals C.2,
+    Huffman-coded requests sharing one dynamic table C.4) and its own malformed-input rejections."""
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "h2_hpack_test")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", os.path.join(HERE, "native", "h2_hpack_test.cpp"),
+                        "-o", exe, "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "PASS" in r.stdout, (r.stdout, r.stderr[-3000:])

@@ -142,3 +142,85 @@ def test_native_daemon_flag_and_start_errors(daemon_env):
     proc.send_signal(signal.SIGINT)
     _, err = proc.communicate(timeout=10)
     assert proc.returncode == 0 and "Failed to start plugin gpu: Register:" in err
+
+
+def test_native_daemon_survives_hostile_peers(daemon_env):
+    """Anything can connect to a unix socket: garbage instead of the preface, truncated and oversized frames,
+    invalid HPACK (bad indices, bad Huffman padding, runaway integers), DATA on unknown streams, window
+    overflow, a flood of random frames.  The daemon must drop such connections, stay up, and keep answering
+    a well-behaved kubelet -- also when rebuilt under ASan/UBSan/TSan (tests/test_sanitizers.py)."""
+    import random
+    import socket
+    import struct
+    V, root, plug_dir = daemon_env
+    kubelet = FakeKubelet(os.path.join(plug_dir, "kubelet.sock"), V)
+    proc = subprocess.Popen([EXE, "-backend=kfd:" + root, "-plugin_dir", plug_dir], stderr=subprocess.PIPE, text=True)
+    sock = os.path.join(plug_dir, "amd.com_gpu")
+    PREFACE = b"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n"
+
+    def frame(ftype, flags, stream, payload):
+        return struct.pack(">I", len(payload))[1:] + bytes([ftype, flags]) + struct.pack(">I", stream) + payload
+
+    def shoot(data, linger=0.05):
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(2.0)
+        s.connect(sock)
+        try:
+            s.sendall(data)
+            time.sleep(linger)
+            try:
+                s.recv(65536)
+            except (socket.timeout, ConnectionError):
+                pass
+        except (BrokenPipeError, ConnectionError):
+            pass
+        finally:
+            s.close()
+
+    try:
+        kubelet.requests.get(timeout=10)
+        assert _wait_for(sock)
+        rng = random.Random(7)
+        hdr_ok = frame(4, 0, 0, b"")                                            # SETTINGS
+        cases = [
+            b"GET / HTTP/1.1\r\n\r\n",                                          # not HTTP/2
+            PREFACE[:10],                                                       # truncated preface, then close
+            PREFACE + b"\xff" * 64,                                             # frame header with a 16 MiB length
+            PREFACE + hdr_ok + frame(1, 0x4, 1, b"\xff\xff\xff\xff\xff\xff\xff\xff\xff\xff\xff\xff"),  # runaway HPACK int
+            PREFACE + hdr_ok + frame(1, 0x4, 1, b"\xbe"),                       # index 62 with an empty dynamic table
+            PREFACE + hdr_ok + frame(1, 0x4, 1, b"\x00\x83\x00\x00\x00\x01a"),  # Huffman name with bad padding
+            PREFACE + hdr_ok + frame(1, 0x4, 1, b"\x00\x05abc"),                # string longer than the block
+            PREFACE + hdr_ok + frame(1, 0x0, 1, b"\x82") + frame(0, 0, 1, b"x"),  # DATA while a header block is open
+            PREFACE + hdr_ok + frame(0, 0x1, 7, b"\x00\x00\x00\x00\x01z"),      # DATA on a stream that never opened
+            PREFACE + hdr_ok + frame(8, 0, 0, b"\x7f\xff\xff\xff") * 4,         # window increments past 2^31
+            PREFACE + hdr_ok + frame(4, 0, 0, b"\x00\x04"),                     # SETTINGS with a bad length
+            PREFACE + hdr_ok + frame(6, 0, 0, b"1234"),                         # PING with a bad length
+            PREFACE + hdr_ok + frame(1, 0x5 | 0x8, 1, b"\xf0" + b"\x82"),       # pad length larger than the payload
+            PREFACE + hdr_ok + frame(1, 0x5, 1, b"\x83\x86\x44\x01/") + frame(3, 0, 1, b"\x00\x00\x00\x08"),  # GET + RST
+        ]
+        for _ in range(40):                                                     # random frame soup
+            blob = PREFACE + hdr_ok
+            for _ in range(rng.randint(1, 12)):
+                blob += frame(rng.randint(0, 12), rng.randint(0, 255), rng.choice([0, 1, 1, 3, 2 ** 31 - 1]),
+                              bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 40))))
+            cases.append(blob)
+        for c in cases:
+            shoot(c)
+            assert proc.poll() is None, proc.stderr.read()[-3000:]
+        # a POST to a real method with an un-framed body: a clean gRPC error, not a crash
+        # and the well-behaved kubelet is still served
+        with grpc.insecure_channel("unix://" + sock) as ch:
+            assert _call(ch, V.GET_OPTIONS, V.Empty(), V.DevicePluginOptions).get_preferred_allocation_available
+            stream = ch.unary_stream(V.LIST_AND_WATCH, request_serializer=lambda m: m.SerializeToString(),
+                                     response_deserializer=V.ListAndWatchResponse.FromString)(V.Empty())
+            assert len(next(stream).devices) == 63
+            stream.cancel()
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        try:
+            _, err = proc.communicate(timeout=10)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+            _, err = proc.communicate()
+        kubelet.server.stop(0)
+    assert proc.returncode == 0, err[-3000:]
