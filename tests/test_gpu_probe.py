@@ -452,3 +452,15 @@ def test_compiled_hosts_on_the_gpu(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         d = json.loads(r.stdout.strip().splitlines()[-1])
         assert d["n_devices"] == 1 and d["aggregate_gbs"] > 4000 and d["response_bytes"] > 0
+
+
+def test_native_daemon_on_the_gpu(P):
+    """b200dp_plugind on the cuda: backend with grpcio as the kubelet: registers, streams the initial list,
+    and every SIGUSR1 heartbeat (HBM pass included) comes back Healthy."""
+    import importlib
+    dp = importlib.import_module("k8s-device-plugin_b200.daemon_probe")
+    if not os.path.exists(dp.DAEMON):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = dp.heartbeat_latency_ms("cuda:devices=0,bytes=%d" % (256 * MiB), iters=30)
+    assert r["n_devices"] == 1 and r["response_bytes"] > 0 and 0.05 < r["median_ms"] < 50.0
