@@ -11,6 +11,7 @@
 #include <signal.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -35,6 +36,7 @@ struct Flags {
     std::string ns = "amd.com";                      // plugin.go:406-408
     double start_retry_wait = 3.0;                   // dpm/manager.go:19
     int link_check = 0;
+    std::string exporter_socket;                     // optional: serve metricssvc.MetricsService here (health.go:36)
 };
 
 // Go's flag package: -name=value, -name value, --name...; bools not needed here
@@ -55,6 +57,7 @@ bool parse_flags(int argc, char** argv, Flags& f, std::string& err) {
         else if (name == "resource_namespace") f.ns = val;
         else if (name == "start_retry_wait") f.start_retry_wait = atof(val.c_str());
         else if (name == "link_check") f.link_check = atoi(val.c_str());
+        else if (name == "exporter_socket") f.exporter_socket = val;
         else { err = "flag provided but not defined: -" + name; return false; }
     }
     if (!f.plugin_dir.empty() && f.plugin_dir.back() != '/') f.plugin_dir += '/';
@@ -246,6 +249,63 @@ private:
     size_t rr_ = 0;
 };
 
+// metricssvc.MetricsService/{List,GetGPUState} (internal/pkg/exporter/metricssvc/metricssvc.pb.go:95-110,284-291;
+// metricssvc_grpc.pb.go:45-46) answered from the HBM probe, so that an UNMODIFIED reference plugin reads B200
+// verdicts through its own exporter client (health.go:42-82): GPUState{ID=1, UUID=2, Health=3 "healthy"|"unhealthy"
+// (health.go:75), AssociatedWorkload=4, Device=5 = the kubelet device id (health.go:98)}.  cuda: backend only.
+class ExporterService {
+public:
+    ExporterService(b2dp_ctx* ctx, std::string path) : ctx_(ctx), path_(std::move(path)) {}
+    bool start(std::string& err) {
+        const size_t slash = path_.rfind('/');
+        if (slash != std::string::npos && slash > 0) ::mkdir(path_.substr(0, slash).c_str(), 0755);
+        server_.add_unary("/metricssvc.MetricsService/List", [this](const std::string&, std::string& out) { return states({}, out); });
+        server_.add_unary("/metricssvc.MetricsService/GetGPUState", [this](const std::string& in, std::string& out) {
+            std::vector<std::string> want;  // GPUGetRequest{ID=1 repeated string}
+            pbread::Reader r(in);
+            int field, wire;
+            while (!r.done()) {
+                if (!r.tag(field, wire)) return h2::Status{h2::GRPC_INTERNAL, "bad GPUGetRequest"};
+                std::string_view b;
+                if (field == 1 && wire == 2) { if (!r.bytes(b)) return h2::Status{h2::GRPC_INTERNAL, "bad GPUGetRequest"}; want.emplace_back(b); }
+                else if (!r.skip(wire)) return h2::Status{h2::GRPC_INTERNAL, "bad GPUGetRequest"};
+            }
+            return states(want, out);
+        });
+        return server_.listen_unix(path_, err);
+    }
+    void stop() { server_.stop(); }
+
+private:
+    h2::Status states(const std::vector<std::string>& want, std::string& out) {
+        std::vector<b2dp_device> devs(64);
+        int n = 0;
+        int rc = b2dp_enumerate(ctx_, devs.data(), (int)devs.size(), &n);
+        if (rc == B2DP_E_NOSPC) { devs.resize((size_t)n); rc = b2dp_enumerate(ctx_, devs.data(), n, &n); }
+        if (rc != B2DP_OK) return {h2::GRPC_UNKNOWN, b2dp_strerror(rc)};
+        std::vector<b2dp_probe_result> res((size_t)n + 1);
+        int m = 0;
+        rc = b2dp_probe_health(ctx_, nullptr, res.data(), (int)res.size(), &m);
+        if (rc != B2DP_OK) return {h2::GRPC_UNKNOWN, std::string(b2dp_strerror(rc)) + ": " + b2dp_last_error(ctx_)};
+        for (int i = 0; i < m; ++i) {
+            const int d = res[(size_t)i].device;
+            if (d < 0 || d >= n) continue;
+            const std::string id = std::to_string(d);
+            if (!want.empty() && std::find(want.begin(), want.end(), id) == want.end()) continue;
+            std::string g;
+            b2dp::pb::string_field(g, 1, id);
+            b2dp::pb::string_field(g, 2, devs[(size_t)d].id);
+            b2dp::pb::string_field(g, 3, res[(size_t)i].healthy ? "healthy" : "unhealthy");
+            b2dp::pb::string_field(g, 5, devs[(size_t)d].id);
+            b2dp::pb::bytes_field(out, 1, g);
+        }
+        return {};
+    }
+    b2dp_ctx* ctx_;
+    std::string path_;
+    h2::GrpcServer server_;
+};
+
 bool sock_identity(const std::string& path, ino_t& ino, long long& ctime_ns) {
     struct stat st;
     if (::stat(path.c_str(), &st) != 0) return false;
@@ -294,6 +354,12 @@ int main(int argc, char** argv) {
     rc = b2dp_resource_list(ctx, fl.strategy.c_str(), names, 64, &n_res);  // main.go:141-146
     if (rc != B2DP_OK) { logf("Error occured: %s", b2dp_strerror(rc)); b2dp_close(ctx); return 1; }
 
+    std::unique_ptr<ExporterService> exporter;
+    if (!fl.exporter_socket.empty()) {
+        exporter = std::make_unique<ExporterService>(ctx, fl.exporter_socket);
+        if (!exporter->start(err)) { logf("exporter socket: %s", err.c_str()); b2dp_close(ctx); return 1; }
+        logf("metricssvc.MetricsService on %s", fl.exporter_socket.c_str());
+    }
     std::vector<std::unique_ptr<Plugin>> plugins;
     auto start_all = [&] {  // dpm handleNewPlugins + startPlugin
         plugins.clear();
@@ -351,6 +417,7 @@ int main(int argc, char** argv) {
     }
     logf("Received signal, exiting");
     plugins.clear();
+    if (exporter) exporter->stop();
     b2dp_close(ctx);
     return 0;
 }

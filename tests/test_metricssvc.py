@@ -71,3 +71,45 @@ def test_metrics_server_on_cuda_backend(pkg, short_dir):
             assert reference_get_gpu_health(srv_mod, sock)[ids[0]] == "Healthy"
         finally:
             server.stop()
+
+
+@pytest.mark.gpu
+def test_native_daemon_serves_the_exporter_contract(pkg, short_dir):
+    """The native daemon's -exporter_socket: the reference's own exporter client (restated above) reads one
+    verdict per kubelet device id, produced by the HBM pass."""
+    import signal
+    import subprocess
+    import time
+    from concurrent import futures
+    srv_mod = importlib.import_module("k8s-device-plugin_b200.server")
+    dp = importlib.import_module("k8s-device-plugin_b200.daemon_probe")
+    V = pkg.v1beta1
+    if not os.path.exists(dp.DAEMON):
+        import __graft_entry__
+        __graft_entry__.build()
+
+    class Kubelet(grpc.GenericRpcHandler):
+        def service(self, det):
+            if det.method != V.REGISTER:
+                return None
+            return grpc.unary_unary_rpc_method_handler(lambda req, ctx: V.Empty().SerializeToString(), lambda b: b, lambda b: b)
+    kubelet = grpc.server(futures.ThreadPoolExecutor(max_workers=2))
+    kubelet.add_generic_rpc_handlers((Kubelet(),))
+    kubelet.add_insecure_port("unix://" + os.path.join(short_dir, "kubelet.sock"))
+    kubelet.start()
+    sock = os.path.join(short_dir, "amdgpu_device_metrics_exporter_grpc.socket")
+    proc = subprocess.Popen([dp.DAEMON, "-backend=cuda:bytes=%d,min_gbs=0.001" % (64 << 20), "-plugin_dir", short_dir,
+                             "-exporter_socket", sock], stderr=subprocess.PIPE, text=True)
+    try:
+        t0 = time.time()
+        while not os.path.exists(sock) and time.time() - t0 < 60 and proc.poll() is None:
+            time.sleep(0.05)
+        with pkg.Context("cuda:bytes=%d" % (1 << 20)) as ctx:
+            ids = sorted(ctx.enumerate())
+        for _ in range(3):
+            assert reference_get_gpu_health(srv_mod, sock) == {i: "Healthy" for i in ids}
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        _, err = proc.communicate(timeout=20)
+        kubelet.stop(0)
+    assert proc.returncode == 0, err[-2000:]

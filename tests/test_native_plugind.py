@@ -224,3 +224,31 @@ def test_native_daemon_survives_hostile_peers(daemon_env):
             _, err = proc.communicate()
         kubelet.server.stop(0)
     assert proc.returncode == 0, err[-3000:]
+
+
+def test_native_daemon_exporter_socket_on_kfd_is_a_clean_error(daemon_env):
+    """-exporter_socket serves metricssvc.MetricsService from the HBM probe; the kfd: backend has no probe and
+    no CPU fallback, so List answers with a gRPC error (the reference's client then uses the default health,
+    health.go:66-69) instead of inventing verdicts."""
+    import importlib
+    srv_mod = importlib.import_module("k8s-device-plugin_b200.server")
+    V, root, plug_dir = daemon_env
+    kubelet = FakeKubelet(os.path.join(plug_dir, "kubelet.sock"), V)
+    exp = os.path.join(plug_dir, "exp", "m.sock")
+    proc = subprocess.Popen([EXE, "-backend=kfd:" + root, "-plugin_dir", plug_dir, "-exporter_socket", exp],
+                            stderr=subprocess.PIPE, text=True)
+    try:
+        kubelet.requests.get(timeout=10)
+        assert _wait_for(exp)
+        with grpc.insecure_channel("unix://" + exp) as ch:
+            call = ch.unary_unary(srv_mod.METRICS_LIST, request_serializer=lambda b: b,
+                                  response_deserializer=srv_mod.GPUStateResponse.FromString)
+            with pytest.raises(grpc.RpcError) as ei:
+                call(b"", timeout=5.0)
+            assert ei.value.code() == grpc.StatusCode.UNKNOWN
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        _, err = proc.communicate(timeout=10)
+        kubelet.server.stop(0)
+    assert proc.returncode == 0, err[-2000:]
+    assert not os.path.exists(exp)
