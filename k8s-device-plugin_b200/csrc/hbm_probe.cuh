@@ -269,6 +269,13 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// HINT template parameter of hbm_probe_tma (tools/probe_sweep only; the product uses 0 = no hints):
+//   bit 0 loads evict_first, bit 1 stores evict_first, bit 2 stores evict_last, bit 3 loads evict_last
 __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
                                               uint64_t pol) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -336,11 +343,12 @@ hbm_probe_tma(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned l
     Acc a;
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
-            const uint64_t pol = HINT ? policy_evict_first() : 0ull;
+            const uint64_t pol_ld = (HINT & 8) ? policy_evict_last() : (HINT & 1) ? policy_evict_first() : 0ull;
+            const uint64_t pol_st = (HINT & 4) ? policy_evict_last() : (HINT & 2) ? policy_evict_first() : 0ull;
             for (int k = 0; k < STAGES && (unsigned long long)k < my_tiles; ++k) {
                 const unsigned long long t = blockIdx.x + (unsigned long long)k * gridDim.x;
                 mbar_expect_tx(&full[k], TILE_BYTES);
-                if (HINT & 1) bulk_g2s_hint(tiles + (size_t)k * TILE_VEC, src + t * TILE_VEC, TILE_BYTES, &full[k], pol);
+                if (HINT & 9) bulk_g2s_hint(tiles + (size_t)k * TILE_VEC, src + t * TILE_VEC, TILE_BYTES, &full[k], pol_ld);
                 else bulk_g2s(tiles + (size_t)k * TILE_VEC, src + t * TILE_VEC, TILE_BYTES, &full[k]);
             }
             for (unsigned long long k = 0; k < my_tiles; ++k) {
@@ -348,7 +356,7 @@ hbm_probe_tma(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned l
                 const uint32_t parity = (uint32_t)((k / STAGES) & 1);
                 const unsigned long long t = blockIdx.x + k * gridDim.x;
                 mbar_wait(&done[slot], parity);
-                if (HINT & 2) bulk_s2g_hint(dst + t * TILE_VEC, tiles + (size_t)slot * TILE_VEC, TILE_BYTES, pol);
+                if (HINT & 6) bulk_s2g_hint(dst + t * TILE_VEC, tiles + (size_t)slot * TILE_VEC, TILE_BYTES, pol_st);
                 else bulk_s2g(dst + t * TILE_VEC, tiles + (size_t)slot * TILE_VEC, TILE_BYTES);
                 bulk_commit();
                 if (k >= 1) {
@@ -358,7 +366,7 @@ hbm_probe_tma(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned l
                         const int sn = (int)(kn % STAGES);
                         const unsigned long long tn = blockIdx.x + kn * gridDim.x;
                         mbar_expect_tx(&full[sn], TILE_BYTES);
-                        if (HINT & 1) bulk_g2s_hint(tiles + (size_t)sn * TILE_VEC, src + tn * TILE_VEC, TILE_BYTES, &full[sn], pol);
+                        if (HINT & 9) bulk_g2s_hint(tiles + (size_t)sn * TILE_VEC, src + tn * TILE_VEC, TILE_BYTES, &full[sn], pol_ld);
                         else bulk_g2s(tiles + (size_t)sn * TILE_VEC, src + tn * TILE_VEC, TILE_BYTES, &full[sn]);
                     }
                 }

@@ -237,6 +237,8 @@ int main(int argc, char** argv) {
     TMAH(4, 1024, 3, 1) TMAH(4, 1024, 3, 2) TMAH(4, 1024, 3, 3) TMAH(4, 512, 6, 3) TMAH(4, 768, 4, 0) TMAH(4, 768, 4, 3)
     TMAH(8, 1024, 3, 0) TMAH(8, 1024, 3, 3) TMAH(2, 1024, 3, 0) TMAH(4, 512, 6, 0) TMAH(4, 1536, 3, 0) TMAH(4, 1280, 3, 0)
     TMAH(4, 896, 3, 0) TMAH(4, 640, 5, 0) TMAH(4, 1024, 4, 3) TMAH(6, 768, 4, 0) TMAH(6, 1536, 3, 0)
+    // hint bits: 1 loads evict_first, 2 stores evict_first, 4 stores evict_last, 8 loads evict_last
+    TMAH(4, 1024, 3, 4) TMAH(4, 1024, 3, 5) TMAH(4, 1024, 3, 8) TMAH(4, 1024, 3, 10) TMAH(4, 1024, 3, 12)
     TMA(4, 512, 4) TMA(4, 1024, 3) TMA(4, 1024, 4) TMA(4, 1024, 6) TMA(4, 2048, 3) TMA(4, 2048, 4)
     TMA(8, 1024, 4) TMA(8, 2048, 3) TMA(8, 2048, 4) TMA(8, 4096, 3) TMA(2, 1024, 4) TMA(2, 512, 6)
 
