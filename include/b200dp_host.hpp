@@ -36,8 +36,12 @@ struct Error {
         Error e;
         e.code = rc;
         if (rc != B2DP_OK) {
-            const char* le = c ? b2dp_last_error(c) : nullptr;
-            e.msg = (le && *le) ? le : b2dp_strerror(rc);
+            e.msg = b2dp_strerror(rc);  // allocator codes: the reference's exact strings
+            // codes whose static text is generic carry the detail recorded by the failing call on this thread
+            const bool generic = rc == B2DP_E_CUDA || rc == B2DP_E_NOGPU || rc == B2DP_E_NODRIVER || rc == B2DP_E_INVAL ||
+                                 rc == B2DP_E_UNSUPPORTED || rc == B2DP_E_IO;
+            const char* le = generic ? b2dp_last_error(c) : nullptr;
+            if (le && *le) e.msg = le;
         }
         return e;
     }
