@@ -135,7 +135,9 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     shrink_bytes=<prefix verified by busy=shrink, default 67108864>, ecc=1 (also fail on new
  *                     uncorrected ECC errors, one NVML query per device per pass), xid=1 (also fail a device
  *                     for good once NVML delivers a critical Xid event for it -- application-level Xids 13, 31,
- *                     43, 45, 68, 109 are ignored; one non-blocking nvmlEventSetWait per pass).
+ *                     43, 45, 68, 109 are ignored; a listener thread waits on the NVML event set and, when a
+ *                     device-level Xid arrives, every running b2dp_watch loop of the context sends a heartbeat
+ *                     cycle at once instead of at its next pulse).
  * B2DP_E_NODRIVER (kfd: driver dir absent) | B2DP_E_NOGPU | B2DP_E_CUDA | B2DP_E_INVAL. */
 B2DP_API int b2dp_open(const char *backend_uri, b2dp_ctx **out);
 B2DP_API void b2dp_close(b2dp_ctx *ctx);

@@ -41,6 +41,7 @@ struct b2dp_ctx {
     std::vector<float> p2p_gbs; // last matrix, n x n
     std::vector<Device> stream_devs;  // the device list of the current ListAndWatch stream
     bool have_stream_devs = false;
+    std::vector<b2dp_watch*> watches;  // running b2dp_watch loops (guarded by mu): a latched Xid beats them all at once
 };
 
 static int fail(int code, const std::string& msg) { t_last_error = msg; return code; }
@@ -156,6 +157,12 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         c->kind = b2dp_ctx::CUDA;
         c->sysroot = cfg.sysroot;
         c->cuda = be;
+        // xid=1: a device-level Xid is pushed to the kubelet at once -- every running ListAndWatch loop of this
+        // context runs a heartbeat cycle now instead of at the next pulse (the reference only learns at a pulse)
+        cuda_set_health_event_callback(be, [c] {
+            std::lock_guard<std::mutex> g(c->mu);
+            for (b2dp_watch* w : c->watches) b2dp_watch_beat(w);
+        });
         *out = c;
         return B2DP_OK;
     }
@@ -482,6 +489,7 @@ extern "C" int b2dp_watch_start(b2dp_ctx* c, const char* resource, uint32_t puls
     w->pulse_ms = pulse_ms;
     w->cb = cb;
     w->user = user;
+    { std::lock_guard<std::mutex> g(c->mu); c->watches.push_back(w); }
     w->th = std::thread(watch_loop, w);
     *out = w;
     return B2DP_OK;
@@ -496,6 +504,11 @@ extern "C" int b2dp_watch_beat(b2dp_watch* w) {
 
 extern "C" void b2dp_watch_stop(b2dp_watch* w) {
     if (!w) return;
+    {
+        std::lock_guard<std::mutex> g(w->ctx->mu);
+        auto& ws = w->ctx->watches;
+        ws.erase(std::remove(ws.begin(), ws.end(), w), ws.end());
+    }
     { std::lock_guard<std::mutex> l(w->mu); w->stop = true; }
     w->cv.notify_all();
     if (w->th.joinable()) w->th.join();

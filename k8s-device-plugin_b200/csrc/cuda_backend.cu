@@ -124,7 +124,7 @@ struct Gpu {
     unsigned long long ecc_base = 0;      // uncorrected volatile ECC count when the context was opened
     bool have_ecc = false;
     bool xid_registered = false;
-    unsigned long long xid_fault = 0;     // first critical Xid seen on this device (sticky, like a real fault)
+    std::atomic<unsigned long long> xid_fault{0};  // first critical Xid seen on this device (sticky, like a real fault)
     int last_healthy = 1;
     // worker
     std::thread th;
@@ -154,8 +154,16 @@ public:
     std::string driver_version, driver_src_version;
     std::mutex probe_mu;  // one fan-out at a time
     std::mutex bc_mu;
-    void* xid_set = nullptr;                         // NVML event set (xid=1)
-    std::deque<std::pair<int, unsigned long long>> xid_injected;  // test hook: (device, xid), guarded by probe_mu
+    void* xid_set = nullptr;                         // NVML event set (xid=1), waited on by xid_thread only
+    std::thread xid_thread;
+    std::atomic<bool> xid_quit{false};
+    std::mutex xid_cb_mu;
+    std::function<void()> on_health_event;           // e.g. "run a heartbeat now on every ListAndWatch stream"
+    void fire_health_event() {
+        std::function<void()> fn;
+        { std::lock_guard<std::mutex> l(xid_cb_mu); fn = on_health_event; }
+        if (fn) fn();
+    }
     std::map<unsigned long long, std::array<unsigned long long, 32>> bitcounts;
     unsigned long long n_vec() const { return cfg.bytes / 16; }
 };
@@ -231,6 +239,8 @@ static std::string read_trim(const std::string& p) {
     if (!go::read_file(p, d)) return "";
     return go::trim_space(d);
 }
+
+static void xid_listener(CudaBackend* be);
 
 int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err) {
     int count = 0;
@@ -325,6 +335,7 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         for (auto& gp : be->gpus)
             if (gp->nvh && be->nvml.register_events(gp->nvh, 0x8ull /*nvmlEventTypeXidCriticalError*/, be->xid_set) == 0)
                 gp->xid_registered = true;
+        be->xid_thread = std::thread(xid_listener, be.get());
     }
 
     // start workers and allocate per-GPU state on them
@@ -377,6 +388,9 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
 
 void cuda_backend_close(CudaBackend* be) {
     if (!be) return;
+    be->xid_quit = true;
+    if (be->xid_thread.joinable()) be->xid_thread.join();
+    { std::lock_guard<std::mutex> l(be->xid_cb_mu); be->on_health_event = nullptr; }
     for (auto& gp : be->gpus) {
         Gpu* g = gp.get();
         if (!g->th.joinable()) continue;
@@ -399,6 +413,10 @@ void cuda_backend_close(CudaBackend* be) {
 
 int cuda_device_count(CudaBackend* be) { return (int)be->gpus.size(); }
 float cuda_min_gbs(CudaBackend* be) { return be->cfg.min_gbs; }
+void cuda_set_health_event_callback(CudaBackend* be, std::function<void()> fn) {
+    std::lock_guard<std::mutex> l(be->xid_cb_mu);
+    be->on_health_event = std::move(fn);
+}
 
 int cuda_enumerate(CudaBackend* be, std::vector<Device>& out, std::string&) {
     out.clear();
@@ -510,22 +528,26 @@ static bool xid_is_application_error(unsigned long long xid) {
     switch (xid) { case 13: case 31: case 43: case 45: case 68: case 109: return true; default: return false; }
 }
 
-// xid=1: drain pending critical-Xid events (non-blocking) and latch them on their device.
-static void drain_xid_events(CudaBackend* be) {
-    auto latch = [&](Gpu* g, unsigned long long xid) {
-        if (!xid_is_application_error(xid) && !g->xid_fault) g->xid_fault = xid ? xid : 999;
-    };
-    while (!be->xid_injected.empty()) {
-        auto ev = be->xid_injected.front();
-        be->xid_injected.pop_front();
-        if (ev.first >= 0 && ev.first < (int)be->gpus.size()) latch(be->gpus[(size_t)ev.first].get(), ev.second);
-    }
-    if (!be->xid_set || !be->nvml.event_wait) return;
+static void latch_xid(Gpu* g, unsigned long long xid) {
+    unsigned long long none = 0;
+    if (!xid_is_application_error(xid)) g->xid_fault.compare_exchange_strong(none, xid ? xid : 999);
+}
+
+// xid=1: the only thread that waits on the NVML event set.  A device-level Xid is latched on its device and
+// reported at once (on_health_event), not at the next pulse.
+static void xid_listener(CudaBackend* be) {
     Nvml::EventData d{};
-    for (int guard = 0; guard < 64 && be->nvml.event_wait(be->xid_set, &d, 0) == 0; ++guard) {
+    while (!be->xid_quit.load()) {
+        const int rc = be->nvml.event_wait(be->xid_set, &d, 200);  // ms; NVML_ERROR_TIMEOUT (10) when idle
+        if (rc != 0) {
+            if (rc != 10) std::this_thread::sleep_for(std::chrono::milliseconds(200));  // a failing set must not spin
+            continue;
+        }
         if (d.type != 0x8ull) continue;  // nvmlEventTypeXidCriticalError
+        bool hit = false;
         for (auto& g : be->gpus)
-            if (g->nvh == d.device) latch(g.get(), d.data);
+            if (g->nvh == d.device && !xid_is_application_error(d.data)) { latch_xid(g.get(), d.data); hit = true; }
+        if (hit) be->fire_health_event();
     }
 }
 
@@ -680,9 +702,8 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         be->gpus[i]->last_healthy = o.healthy;
     }
     if (be->cfg.check_xid) {  // opt-in: a critical Xid since open fails the device whatever the pass said
-        drain_xid_events(be);
         for (size_t i = 0; i < n; ++i)
-            if (be->gpus[i]->xid_fault) {
+            if (be->gpus[i]->xid_fault.load()) {
                 out[i].flags |= B2DP_RES_XID;
                 out[i].healthy = 0;
                 be->gpus[i]->last_healthy = 0;
@@ -701,7 +722,10 @@ int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask,
     Gpu* g = gpu_at(be, device, err);
     if (!g) return B2DP_E_INVAL;
     if (word == ~0ull) {  // synthetic critical-Xid event `mask`, handled like one delivered by NVML (xid=1)
-        if (be->cfg.check_xid) be->xid_injected.emplace_back(device, (unsigned long long)mask);
+        if (be->cfg.check_xid && !xid_is_application_error(mask)) {
+            latch_xid(g, mask);
+            be->fire_health_event();
+        }
         return B2DP_OK;
     }
     if (word >= be->n_vec() * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
@@ -720,7 +744,7 @@ int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
     for (int i = 0; i < (int)be->gpus.size(); ++i) {
         if (device >= 0 && device != i) continue;
         Gpu* g = be->gpus[i].get();
-        g->xid_fault = 0;  // operator acknowledgement: a latched Xid is cleared together with the buffers
+        g->xid_fault.store(0);  // operator acknowledgement: a latched Xid is cleared together with the buffers
         cudaError_t ce = cudaSuccess;
         run_sync(g, [&] {
             hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);

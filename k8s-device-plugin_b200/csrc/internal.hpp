@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -113,5 +114,7 @@ int cuda_p2p_matrix(CudaBackend*, const b2dp_p2p_opts* opts, float* gbs, int32_t
 int cuda_device_count(CudaBackend*);
 void cuda_label_source(CudaBackend*, LabelSource& src);
 float cuda_min_gbs(CudaBackend*);
+// xid=1: called (from a backend thread, or from b2dp_probe_inject_fault) when a device-level Xid has been latched
+void cuda_set_health_event_callback(CudaBackend*, std::function<void()> fn);
 
 }  // namespace b2dp

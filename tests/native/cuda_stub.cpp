@@ -16,4 +16,5 @@ int cuda_p2p_matrix(CudaBackend*, const b2dp_p2p_opts*, float*, int32_t*, uint64
 int cuda_device_count(CudaBackend*) { return 0; }
 void cuda_label_source(CudaBackend*, LabelSource&) {}
 float cuda_min_gbs(CudaBackend*) { return 0.f; }
+void cuda_set_health_event_callback(CudaBackend*, std::function<void()>) {}
 }  // namespace b2dp

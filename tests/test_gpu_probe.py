@@ -464,3 +464,26 @@ def test_native_daemon_on_the_gpu(P):
         __graft_entry__.build()
     r = dp.heartbeat_latency_ms("cuda:devices=0,bytes=%d" % (256 * MiB), iters=30)
     assert r["n_devices"] == 1 and r["response_bytes"] > 0 and 0.05 < r["median_ms"] < 50.0
+
+
+def test_xid_is_pushed_to_the_stream_at_once(P):
+    """xid=1 with a running ListAndWatch loop and NO ticker: a device-level Xid makes every stream of the
+    context run a heartbeat cycle immediately (the reference would only notice at its next pulse).  The
+    synthetic event goes through the same latch + notification as one read from the NVML event set."""
+    import queue
+    UINT64_MAX = (1 << 64) - 1
+    got = queue.Queue()
+    with _open(P, 16 * MiB, ",xid=1") as ctx:
+        w = ctx.watch(lambda rc, wire, st: got.put((rc, wire, st)), pulse_ms=0, min_gbs=1e-3)
+        try:
+            rc, wire, st = got.get(timeout=10)                       # initial list
+            assert rc == 0 and P.v1beta1.ListAndWatchResponse.FromString(wire).devices[0].health == "Healthy"
+            ctx.probe_inject_fault(0, UINT64_MAX, 31)                # application-level: nothing happens
+            with pytest.raises(queue.Empty):
+                got.get(timeout=0.5)
+            ctx.probe_inject_fault(0, UINT64_MAX, 79)                # fallen off the bus
+            rc, wire, st = got.get(timeout=5)                        # pushed without any beat()
+            assert rc == 0 and st.n_unhealthy == 1
+            assert P.v1beta1.ListAndWatchResponse.FromString(wire).devices[0].health == "Unhealthy"
+        finally:
+            w.stop()
