@@ -252,3 +252,54 @@ def test_native_daemon_exporter_socket_on_kfd_is_a_clean_error(daemon_env):
         kubelet.server.stop(0)
     assert proc.returncode == 0, err[-2000:]
     assert not os.path.exists(exp)
+
+
+def test_native_daemon_soak_streams_come_and_go(daemon_env):
+    """A kubelet that reconnects over and over (each time: options, a ListAndWatch stream, a few heartbeats,
+    an allocation, cancel) next to a storm of SIGUSR1 heartbeats: answers stay right, finished streams are
+    reaped (no growing thread count), memory stays flat; under ASan the exit-time leak check runs as well."""
+    V, root, plug_dir = daemon_env
+    kubelet = FakeKubelet(os.path.join(plug_dir, "kubelet.sock"), V)
+    proc = subprocess.Popen([EXE, "-backend=kfd:" + root, "-plugin_dir", plug_dir], stderr=subprocess.PIPE, text=True)
+    sock = os.path.join(plug_dir, "amd.com_gpu")
+
+    def threads_and_rss():
+        with open("/proc/%d/status" % proc.pid) as f:
+            st = dict(line.split(":", 1) for line in f if ":" in line)
+        return int(st["Threads"].split()[0]), int(st["VmRSS"].split()[0])
+
+    try:
+        kubelet.requests.get(timeout=10)
+        assert _wait_for(sock)
+        marks = []
+        for it in range(60):
+            with grpc.insecure_channel("unix://" + sock) as ch:
+                assert _call(ch, V.GET_OPTIONS, V.Empty(), V.DevicePluginOptions).get_preferred_allocation_available
+                stream = ch.unary_stream(V.LIST_AND_WATCH, request_serializer=lambda m: m.SerializeToString(),
+                                         response_deserializer=V.ListAndWatchResponse.FromString)(V.Empty())
+                first = next(stream)
+                assert len(first.devices) == 63
+                for _ in range(5):
+                    proc.send_signal(signal.SIGUSR1)
+                    assert len(next(stream).devices) == 63
+                ids = [d.ID for d in first.devices]
+                areq = V.AllocateRequest(container_requests=[V.ContainerAllocateRequest(devices_ids=ids[:3])])
+                assert len(_call(ch, V.ALLOCATE, areq, V.AllocateResponse).container_responses[0].devices) == 7
+                stream.cancel()
+            if it in (9, 59):
+                proc.send_signal(signal.SIGUSR1)        # lets the daemon reap cancelled streams
+                time.sleep(0.2)
+                marks.append(threads_and_rss())
+        (t0, rss0), (t1, rss1) = marks
+        assert t1 <= t0 + 4, marks                       # watch / connection threads do not accumulate
+        if "B200DP_PLUGIND" not in os.environ:           # sanitizer builds: ASan's quarantine keeps freed memory mapped;
+            assert rss1 <= rss0 * 1.5 + 8192, marks      # (kB) their exit-time leak check is the memory test there
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        try:
+            _, err = proc.communicate(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+            _, err = proc.communicate()
+        kubelet.server.stop(0)
+    assert proc.returncode == 0, err[-3000:]
