@@ -199,6 +199,8 @@ typedef struct b2dp_probe_result {
 #define B2DP_RES_SKIPPED_BUSY 0x1u /* busy=skip: another process owns the GPU, no pass ran, the last verdict stands */
 #define B2DP_RES_SHRUNK 0x2u       /* busy=shrink: a prefix (shrink_bytes) was verified without re-keying; no GB/s floor */
 #define B2DP_RES_ECC 0x4u          /* ecc=1: NVML reports new uncorrected ECC errors since open => Unhealthy */
+#define B2DP_RES_SMALL_RING 0x10u  /* HBM was short when the context opened (e.g. a restart under running pods): the ring
+                                      slots on this GPU are smaller than bytes=; `bytes` reports what a pass moved; no GB/s floor */
 #define B2DP_RES_XID 0x8u          /* xid=1: a critical Xid event was delivered for this device since open (or the
                                       last b2dp_probe_reset) => Unhealthy, sticky */
 

@@ -35,7 +35,7 @@ E_ALLOC_SUBSET_SIZE, E_ALLOC_SUBSET_AVAIL = -28, -29
 PROBE_VARIANT_TMA, PROBE_VARIANT_R128 = 0, 1
 PROBE_VIA_WORKERS = 0x10
 PROBE_EVENT_TIMING = 0x20
-RES_SKIPPED_BUSY, RES_SHRUNK, RES_ECC, RES_XID = 1, 2, 4, 8
+RES_SKIPPED_BUSY, RES_SHRUNK, RES_ECC, RES_XID, RES_SMALL_RING = 1, 2, 4, 8, 16
 LW_INITIAL, LW_HEARTBEAT, LW_EXTERNAL_SOURCE, LW_NO_PROBE, LW_LINK_CHECK = 1, 2, 4, 8, 16
 
 Id64 = C.c_char * 64

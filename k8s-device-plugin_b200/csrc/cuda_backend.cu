@@ -134,6 +134,8 @@ struct Gpu {
     bool quit = false;
     // state owned by the worker thread
     std::vector<uint4*> buf;            // ring of cfg.slots buffers: pass k reads buf[cur], writes buf[next()]
+    unsigned long long n_vec = 0;       // 16-byte vectors per slot on THIS GPU (cfg.bytes / 16 unless HBM was short at open)
+    bool small_ring = false;            // slots had to be smaller than requested: passes carry no GB/s floor
     ProbeCtl* ctl = nullptr;
     ProbeOut *out_h = nullptr, *out_d = nullptr;
     cudaStream_t stream = nullptr;
@@ -165,7 +167,6 @@ public:
         if (fn) fn();
     }
     std::map<unsigned long long, std::array<unsigned long long, 32>> bitcounts;
-    unsigned long long n_vec() const { return cfg.bytes / 16; }
 };
 
 static std::string cuda_err(const char* what, cudaError_t e) {
@@ -348,13 +349,27 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         const unsigned long long bytes = cfg.bytes, n_vec = cfg.bytes / 16;
         const int idx = (int)i;
         g->buf.assign((size_t)cfg.slots, nullptr);
-        cs.push_back(post(g, [g, bytes, n_vec, idx, &errs, &where] {
+        (void)n_vec;
+        cs.push_back(post(g, [g, bytes, idx, &errs, &where] {
             cudaError_t e;
 #define TRY(x) if ((e = (x)) != cudaSuccess) { errs[idx] = e; where[idx] = #x; return; }
             TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
             TRY(cudaEventCreate(&g->e0));
             TRY(cudaEventCreate(&g->e1));
-            for (auto& b : g->buf) TRY(cudaMalloc(&b, bytes));
+            // HBM may be short when the daemon restarts under running pods: rather than fail (and take the node's
+            // GPUs away from the kubelet) halve the slot size until the ring fits, down to 1 MiB
+            unsigned long long slot = bytes;
+            for (;;) {
+                e = cudaSuccess;
+                for (auto& b : g->buf) if ((e = cudaMalloc(&b, slot)) != cudaSuccess) break;
+                if (e == cudaSuccess) break;
+                cudaGetLastError();
+                for (auto& b : g->buf) { if (b) cudaFree(b); b = nullptr; }
+                if (e != cudaErrorMemoryAllocation || slot <= (1ull << 20)) { errs[idx] = e; where[idx] = "cudaMalloc(probe ring)"; return; }
+                slot = (slot / 2) & ~15ull;
+            }
+            g->n_vec = slot / 16;
+            g->small_ring = slot < bytes;
             TRY(cudaMalloc(&g->ctl, sizeof(ProbeCtl)));
             ProbeCtl init{};
             init.first_bad = ~0ull; init.t_start_ns = ~0ull;
@@ -368,7 +383,7 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             g->seed = 0x5EED0000u | (uint32_t)(idx & 0xffff);
             g->cur = 0;
-            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[0], n_vec, g->seed);
+            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[0], g->n_vec, g->seed);
             TRY(cudaGetLastError());
             TRY(cudaStreamSynchronize(g->stream));
 #undef TRY
@@ -474,9 +489,9 @@ static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uin
 }
 
 // Enqueue one pass on g's stream (caller must have made g's device current).
-static void probe_issue(Gpu* g, ProbeJobResult* r, unsigned long long n_vec_full, uint32_t variant) {
+static void probe_issue(Gpu* g, ProbeJobResult* r, uint32_t variant) {
     const uint32_t seed = g->seed, next = seed * 1664525u + 1013904223u;
-    const unsigned long long n_vec = r->n_vec ? r->n_vec : n_vec_full;
+    const unsigned long long n_vec = r->n_vec ? r->n_vec : g->n_vec;
     r->n_vec = n_vec;
     r->seed = seed;
     r->seq = ++g->seq;
@@ -494,7 +509,8 @@ static inline bool probe_published(const Gpu* g, const ProbeJobResult* r) {
 }
 
 // After the pass completed: read the published result, advance the seed / ping-pong state.
-static void probe_collect(Gpu* g, ProbeJobResult* r, unsigned long long n_vec) {
+static void probe_collect(Gpu* g, ProbeJobResult* r) {
+    const unsigned long long n_vec = g->n_vec;  // repairs re-fill the whole slot
     cudaError_t e = r->ce;
     if (e == cudaSuccess && r->timed) {
         e = cudaEventSynchronize(g->e1);  // the result is already published; the event follows within ~1 us
@@ -553,10 +569,7 @@ static void xid_listener(CudaBackend* be) {
 
 int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_probe_result>& out, std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
-    const unsigned long long n_vec = be->n_vec(), n_words = n_vec * 4;
-    std::array<unsigned long long, 32> bc;
-    int rc = get_bitcounts(be, n_words, bc, err);
-    if (rc != B2DP_OK) return rc;
+    int rc = B2DP_OK;
     const uint32_t variant = opts ? (opts->flags & B2DP_PROBE_VARIANT_MASK) : 0;
     const bool via_workers = opts && (opts->flags & B2DP_PROBE_VIA_WORKERS);
     const bool timed = opts && (opts->flags & B2DP_PROBE_EVENT_TIMING);
@@ -581,7 +594,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             if (be->cfg.busy_policy == 1) { state[i] = 3; rflags[i] = B2DP_RES_SKIPPED_BUSY; }
             else {
                 unsigned long long sv = be->cfg.shrink_bytes / 16;
-                res[i]->n_vec = sv < n_vec ? (sv ? sv : 1) : n_vec;
+                res[i]->n_vec = sv < g->n_vec ? (sv ? sv : 1) : g->n_vec;
                 res[i]->advance = false;
                 rflags[i] = B2DP_RES_SHRUNK;
             }
@@ -597,10 +610,10 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             if (state[i] != 0) continue;
             if (g->inflight.load()) { state[i] = 2; continue; }
             g->inflight.store(true);  // until collected: a pass that misses the deadline still owns seed/ring state
-            cs[i] = post(g, [g, r, n_vec, variant] {
-                probe_issue(g, r.get(), n_vec, variant);
+            cs[i] = post(g, [g, r, variant] {
+                probe_issue(g, r.get(), variant);
                 if (r->ce == cudaSuccess) r->ce = cudaStreamSynchronize(g->stream);
-                probe_collect(g, r.get(), n_vec);
+                probe_collect(g, r.get());
                 g->inflight.store(false);
             });
         }
@@ -618,7 +631,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             if (state[i] != 0) continue;
             if (g->inflight.load()) { state[i] = 2; continue; }
             cudaSetDevice(g->ordinal);
-            probe_issue(g, res[i].get(), n_vec, variant);
+            probe_issue(g, res[i].get(), variant);
         }
         size_t pending = 0;
         for (size_t i = 0; i < n; ++i) pending += state[i] == 0;
@@ -636,7 +649,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
                     if (q != cudaSuccess) res[i]->ce = q;
                 }
                 cudaSetDevice(g->ordinal);
-                probe_collect(g, res[i].get(), n_vec);
+                probe_collect(g, res[i].get());
                 state[i] = 1;
                 --pending;
             }
@@ -648,9 +661,9 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             Gpu* g = be->gpus[i].get();
             auto r = res[i];
             g->inflight.store(true);
-            post(g, [g, r, n_vec] {
+            post(g, [g, r] {
                 if (r->ce == cudaSuccess) r->ce = cudaStreamSynchronize(g->stream);
-                probe_collect(g, r.get(), n_vec);
+                probe_collect(g, r.get());
                 g->inflight.store(false);
             });
         }
@@ -661,9 +674,9 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     for (size_t i = 0; i < n; ++i) {
         b2dp_probe_result& o = out[i];
         o.device = (int)i;
-        o.bytes = 2ull * be->cfg.bytes;
+        o.bytes = 2ull * be->gpus[i]->n_vec * 16;
         o.first_bad_word = ~0ull;
-        o.flags = rflags[i];
+        o.flags = rflags[i] | (be->gpus[i]->small_ring ? B2DP_RES_SMALL_RING : 0u);
         if (state[i] == 2) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; be->gpus[i]->last_healthy = 0; continue; }
         if (state[i] == 3) { o.bytes = 0; o.healthy = be->gpus[i]->last_healthy; continue; }  // skipped: last verdict stands
         const ProbeJobResult& r = *res[i];
@@ -674,10 +687,9 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             err = cuda_err("probe", r.ce) + " on " + be->gpus[i]->dev.id;
             continue;
         }
-        if (r.n_vec == n_vec) o.expected_checksum = expected_checksum(bc, n_words, r.seed);
-        else {
-            std::array<unsigned long long, 32> bcs;
-            if (get_bitcounts(be, r.n_vec * 4, bcs, err) != B2DP_OK) { o.err = B2DP_E_CUDA; o.healthy = 0; continue; }
+        {
+            std::array<unsigned long long, 32> bcs;  // cached per size
+            if ((rc = get_bitcounts(be, r.n_vec * 4, bcs, err)) != B2DP_OK) { o.err = B2DP_E_CUDA; o.healthy = 0; continue; }
             o.expected_checksum = expected_checksum(bcs, r.n_vec * 4, r.seed);
             o.bytes = 2ull * r.n_vec * 16;
         }
@@ -690,7 +702,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.gbs = ms_for_rate > 0 ? (float)((double)o.bytes / (double)ms_for_rate * 1e-6) : 0.f;
         // verdict (oracle/probe.py probe_healthy)
         // a shrunk pass shares the GPU with a tenant: integrity only, no bandwidth floor
-        const bool fast_enough = (o.flags & B2DP_RES_SHRUNK) ? true : o.gbs >= min_gbs;
+        const bool fast_enough = (o.flags & (B2DP_RES_SHRUNK | B2DP_RES_SMALL_RING)) ? true : o.gbs >= min_gbs;
         o.healthy = (r.seq_ok && o.mismatches == 0 && o.checksum == o.expected_checksum && fast_enough) ? 1 : 0;
         if (be->cfg.check_ecc && be->gpus[i]->have_ecc) {  // opt-in: an NVML query per device per pass
             unsigned long long now = 0;
@@ -728,7 +740,7 @@ int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask,
         }
         return B2DP_OK;
     }
-    if (word >= be->n_vec() * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
+    if (word >= g->n_vec * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
     cudaError_t ce = cudaSuccess;
     run_sync(g, [&] {
         hbm_poke<<<1, 1, 0, g->stream>>>(reinterpret_cast<uint32_t*>(g->buf[g->cur]), word, mask);
@@ -740,14 +752,13 @@ int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask,
 
 int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
-    const unsigned long long n_vec = be->n_vec();
     for (int i = 0; i < (int)be->gpus.size(); ++i) {
         if (device >= 0 && device != i) continue;
         Gpu* g = be->gpus[i].get();
         g->xid_fault.store(0);  // operator acknowledgement: a latched Xid is cleared together with the buffers
         cudaError_t ce = cudaSuccess;
         run_sync(g, [&] {
-            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
+            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], g->n_vec, g->seed);
             ce = cudaStreamSynchronize(g->stream);
         });
         if (ce != cudaSuccess) { err = cuda_err("hbm_fill", ce); return B2DP_E_CUDA; }
@@ -760,7 +771,7 @@ int cuda_probe_peek(CudaBackend* be, int device, uint64_t word, uint32_t* out, u
     std::lock_guard<std::mutex> pl(be->probe_mu);
     Gpu* g = gpu_at(be, device, err);
     if (!g) return B2DP_E_INVAL;
-    if (word + n > be->n_vec() * 4) { err = "range out of bounds"; return B2DP_E_INVAL; }
+    if (word + n > g->n_vec * 4) { err = "range out of bounds"; return B2DP_E_INVAL; }
     cudaError_t ce = cudaSuccess;
     run_sync(g, [&] {
         ce = cudaMemcpyAsync(out, reinterpret_cast<const uint32_t*>(g->buf[g->cur]) + word, n * 4, cudaMemcpyDeviceToHost,
@@ -779,7 +790,7 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
     std::lock_guard<std::mutex> pl(be->probe_mu);
     if (n != (int)be->gpus.size()) { err = "n must equal the device count"; return B2DP_E_INVAL; }
     unsigned long long bytes = opts && opts->bytes ? opts->bytes : be->cfg.p2p_bytes;
-    if (bytes > be->cfg.bytes) bytes = be->cfg.bytes;
+    for (auto& g : be->gpus) bytes = std::min<unsigned long long>(bytes, g->n_vec * 16);  // the smallest ring slot bounds a pass
     bytes &= ~15ull;
     const unsigned long long n_vec = bytes / 16;
     const int iters = opts && opts->iters ? (int)opts->iters : 2;

@@ -487,3 +487,42 @@ def test_xid_is_pushed_to_the_stream_at_once(P):
             assert P.v1beta1.ListAndWatchResponse.FromString(wire).devices[0].health == "Unhealthy"
         finally:
             w.stop()
+
+
+def test_ring_shrinks_when_hbm_is_short_at_open(P):
+    """A daemon restart under running pods finds HBM mostly taken.  Opening must not fail (that would take the
+    node's GPUs away from the kubelet): the ring slots are halved until they fit, passes stay bit-exact on the
+    smaller slots, carry B2DP_RES_SMALL_RING and no GB/s floor."""
+    import subprocess
+    import sys
+    import torch
+    free, total = torch.cuda.mem_get_info(0)
+    want = 4 << 30                                                   # requested slot size; 2 slots = 8 GiB
+    leave = 5 << 30                                                  # what the "pod" leaves free: < 8 GiB, > 2 x 2 GiB
+    if free < leave + (8 << 30):
+        pytest.skip("GPU already busy")
+    helper = subprocess.Popen([sys.executable, "-c",
+                               "import torch,time,sys; f,_=torch.cuda.mem_get_info(0); "
+                               "x=torch.empty(f-%d, dtype=torch.uint8, device='cuda:0'); print('ready', flush=True); time.sleep(120)" % leave],
+                              stdout=subprocess.PIPE, text=True)
+    try:
+        assert helper.stdout.readline().strip() == "ready"
+        with _open(P, want) as ctx:
+            seed = oprobe.initial_seed(0)
+            for _ in range(3):
+                (r,) = ctx.probe_health(min_gbs=1e9)                 # an impossible floor: must not apply
+                slot = r.bytes // 2
+                assert r.flags & P._native.RES_SMALL_RING and slot in (want // 2, want // 4) and r.err == 0
+                assert r.healthy and r.mismatches == 0 and r.seed == seed
+                assert r.checksum == r.expected_checksum == oprobe.expected_checksum(slot // 4, seed)
+                seed = oprobe.next_seed(seed)
+            n_check = 1 << 18
+            assert np.array_equal(ctx.probe_peek(0, slot // 4 - n_check, n_check), oprobe.pattern(n_check, seed, slot // 4 - n_check))
+            with pytest.raises(P._native.B2dpError):
+                ctx.probe_peek(0, slot // 4 - 1, 2)                  # bounds follow the real slot size
+            ctx.probe_inject_fault(0, slot // 4 - 1, 1)
+            (r,) = ctx.probe_health(min_gbs=1e9)
+            assert not r.healthy and r.mismatches == 1 and r.first_bad_word == slot // 4 - 1
+    finally:
+        helper.kill()
+        helper.wait()
