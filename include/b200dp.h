@@ -138,6 +138,9 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     43, 45, 68, 109 are ignored; a listener thread waits on the NVML event set and, when a
  *                     device-level Xid arrives, every running b2dp_watch loop of the context sends a heartbeat
  *                     cycle at once instead of at its next pulse).
+ *                     A GPU whose own setup fails (or that break=<i>+<j>, a test hook, names by enumeration index)
+ *                     stays in the device list and is reported Unhealthy with B2DP_E_CUDA on every pass; the open
+ *                     only fails when no GPU could be set up.
  * B2DP_E_NODRIVER (kfd: driver dir absent) | B2DP_E_NOGPU | B2DP_E_CUDA | B2DP_E_INVAL. */
 B2DP_API int b2dp_open(const char *backend_uri, b2dp_ctx **out);
 B2DP_API void b2dp_close(b2dp_ctx *ctx);

@@ -145,6 +145,15 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             } else if (p.first == "shrink_bytes") cfg.shrink_bytes = strtoull(p.second.c_str(), nullptr, 0);
             else if (p.first == "ecc") cfg.check_ecc = p.second != "0";
             else if (p.first == "xid") cfg.check_xid = p.second != "0";
+            else if (p.first == "break") {
+                size_t pos = 0;
+                while (pos <= p.second.size()) {
+                    size_t e = p.second.find('+', pos);
+                    if (e == std::string::npos) e = p.second.size();
+                    if (e > pos) cfg.break_devices.push_back(atoi(p.second.substr(pos, e - pos).c_str()));
+                    pos = e + 1;
+                }
+            }
             else return fail(B2DP_E_INVAL, "unknown cuda: option " + p.first);
         }
         if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");

@@ -136,6 +136,8 @@ struct Gpu {
     std::vector<uint4*> buf;            // ring of cfg.slots buffers: pass k reads buf[cur], writes buf[next()]
     unsigned long long n_vec = 0;       // 16-byte vectors per slot on THIS GPU (cfg.bytes / 16 unless HBM was short at open)
     bool small_ring = false;            // slots had to be smaller than requested: passes carry no GB/s floor
+    bool broken = false;                // per-GPU setup failed at open: listed, never probed, always Unhealthy
+    std::string broken_reason;
     ProbeCtl* ctl = nullptr;
     ProbeOut *out_h = nullptr, *out_d = nullptr;
     cudaStream_t stream = nullptr;
@@ -390,13 +392,25 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         }));
     }
     for (auto& c : cs) c->wait();
-    for (size_t i = 0; i < errs.size(); ++i)
-        if (errs[i] != cudaSuccess) {
-            err = cuda_err(where[i], errs[i]) + " on " + be->gpus[i]->dev.id;
-            CudaBackend* raw = be.release();
-            cuda_backend_close(raw);
-            return B2DP_E_CUDA;
-        }
+    // One GPU that cannot be set up (fallen off the bus, exclusive-process mode held by a tenant, no memory at
+    // all) must not take the node's other GPUs away from the kubelet: it stays in the device list and is
+    // reported Unhealthy on every heartbeat.  Only a node with no usable GPU fails to open.
+    size_t n_broken = 0;
+    for (size_t i = 0; i < errs.size(); ++i) {
+        const bool forced = std::find(cfg.break_devices.begin(), cfg.break_devices.end(), (int)i) != cfg.break_devices.end();
+        if (errs[i] == cudaSuccess && !forced) continue;
+        Gpu* g = be->gpus[i].get();
+        g->broken = true;
+        g->broken_reason = forced ? "setup failure injected (break=)" : cuda_err(where[i], errs[i]);
+        g->last_healthy = 0;
+        err = g->broken_reason + " on " + g->dev.id;
+        ++n_broken;
+    }
+    if (n_broken == be->gpus.size()) {
+        CudaBackend* raw = be.release();
+        cuda_backend_close(raw);
+        return B2DP_E_CUDA;
+    }
     *out = be.release();
     return B2DP_OK;
 }
@@ -581,13 +595,14 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     std::vector<char> state(n, 0);  // 0 pending, 1 done, 2 timed out / busy
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
     for (size_t i = 0; i < n; ++i) { res[i] = std::make_shared<ProbeJobResult>(); res[i]->timed = timed; }
+    for (size_t i = 0; i < n; ++i) if (be->gpus[i]->broken) state[i] = 4;  // never launched on
     // busy policy (tenant workloads): a 2 GiB-traffic probe steals bandwidth from a pod that owns the
     // GPU; `busy=skip` keeps the last verdict, `busy=shrink` verifies a small prefix without re-keying
     std::vector<uint32_t> rflags(n, 0);
     if (be->cfg.busy_policy != 0 && be->nvml.ok && be->nvml.running_procs) {
         for (size_t i = 0; i < n; ++i) {
             Gpu* g = be->gpus[i].get();
-            if (!g->nvh) continue;
+            if (!g->nvh || state[i] != 0) continue;
             unsigned cnt = 0;
             const int nrc = be->nvml.running_procs(g->nvh, &cnt, nullptr);  // count only (INSUFFICIENT_SIZE = 7)
             if ((nrc != 0 && nrc != 7) || cnt <= 1) continue;              // this process holds one context itself
@@ -679,6 +694,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.flags = rflags[i] | (be->gpus[i]->small_ring ? B2DP_RES_SMALL_RING : 0u);
         if (state[i] == 2) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; be->gpus[i]->last_healthy = 0; continue; }
         if (state[i] == 3) { o.bytes = 0; o.healthy = be->gpus[i]->last_healthy; continue; }  // skipped: last verdict stands
+        if (state[i] == 4) { o.bytes = 0; o.err = B2DP_E_CUDA; o.healthy = 0; err = be->gpus[i]->broken_reason + " on " + be->gpus[i]->dev.id; continue; }
         const ProbeJobResult& r = *res[i];
         o.seed = r.seed;
         if (r.ce != cudaSuccess) {
@@ -726,6 +742,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
 
 static Gpu* gpu_at(CudaBackend* be, int device, std::string& err) {
     if (device < 0 || device >= (int)be->gpus.size()) { err = "device index out of range"; return nullptr; }
+    if (be->gpus[device]->broken) { err = "device was not set up: " + be->gpus[device]->broken_reason; return nullptr; }
     return be->gpus[device].get();
 }
 
@@ -755,6 +772,7 @@ int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
     for (int i = 0; i < (int)be->gpus.size(); ++i) {
         if (device >= 0 && device != i) continue;
         Gpu* g = be->gpus[i].get();
+        if (g->broken) continue;
         g->xid_fault.store(0);  // operator acknowledgement: a latched Xid is cleared together with the buffers
         cudaError_t ce = cudaSuccess;
         run_sync(g, [&] {
@@ -790,7 +808,7 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
     std::lock_guard<std::mutex> pl(be->probe_mu);
     if (n != (int)be->gpus.size()) { err = "n must equal the device count"; return B2DP_E_INVAL; }
     unsigned long long bytes = opts && opts->bytes ? opts->bytes : be->cfg.p2p_bytes;
-    for (auto& g : be->gpus) bytes = std::min<unsigned long long>(bytes, g->n_vec * 16);  // the smallest ring slot bounds a pass
+    for (auto& g : be->gpus) if (!g->broken) bytes = std::min<unsigned long long>(bytes, g->n_vec * 16);  // the smallest ring slot bounds a pass
     bytes &= ~15ull;
     const unsigned long long n_vec = bytes / 16;
     const int iters = opts && opts->iters ? (int)opts->iters : 2;
@@ -808,6 +826,7 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
         for (int j = 0; j < n; ++j) {
             if (i == j) continue;
             int c = 0;
+            if (be->gpus[i]->broken || be->gpus[j]->broken) continue;
             cudaDeviceCanAccessPeer(&c, be->gpus[i]->ordinal, be->gpus[j]->ordinal);
             can[(size_t)i * n + j] = (char)c;
             if (c && !be->gpus[i]->peer_enabled[j]) {

@@ -100,6 +100,7 @@ struct CudaConfig {
     uint64_t shrink_bytes = 64ull << 20;
     bool check_ecc = false;
     bool check_xid = false;
+    std::vector<int> break_devices;      // test hook: indices (enumeration order) whose per-GPU setup is treated as failed
 };
 int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err);
 void cuda_backend_close(CudaBackend*);

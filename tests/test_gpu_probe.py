@@ -526,3 +526,29 @@ def test_ring_shrinks_when_hbm_is_short_at_open(P):
     finally:
         helper.kill()
         helper.wait()
+
+
+def test_one_unusable_gpu_does_not_take_the_node_down(P):
+    """A GPU whose setup fails at open (simulated with the break= hook) stays in the device list and is sent
+    Unhealthy on every heartbeat; the others keep being probed, allocated and linked.  Only a node with no usable
+    GPU fails to open."""
+    import torch
+    n = torch.cuda.device_count()
+    with pytest.raises(P._native.B2dpError) as ei:
+        P.Context("cuda:devices=0,bytes=%d,break=0" % (16 * MiB))
+    assert ei.value.code == P._native.E_CUDA
+    if n < 2:
+        pytest.skip("needs 2 GPUs for the partial-failure half")
+    with P.Context("cuda:devices=0+1,bytes=%d,p2p_bytes=%d,break=1" % (64 * MiB, 16 * MiB)) as ctx:
+        ids = sorted(ctx.enumerate())
+        assert len(ids) == 2                                          # still listed
+        res = ctx.probe_health(min_gbs=1e-3)
+        assert [(r.healthy, r.err) for r in res] == [(True, 0), (False, P._native.E_CUDA)] and res[1].bytes == 0
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT, min_gbs=1e-3)
+        msg = P.v1beta1.ListAndWatchResponse.FromString(wire)
+        assert [(d.ID, d.health) for d in msg.devices] == [(ids[0], "Healthy"), (ids[1], "Unhealthy")] and st.n_unhealthy == 1
+        with pytest.raises(P._native.B2dpError):
+            ctx.probe_peek(1, 0, 16)
+        assert np.array_equal(ctx.probe_peek(0, 0, 16), oprobe.pattern(16, oprobe.next_seed(oprobe.next_seed(oprobe.initial_seed(0)))))
+        gbs, lt, mm = ctx.p2p_matrix()
+        assert lt[0][1] == 0 and lt[1][0] == 0                        # no link measured to or from the broken GPU
