@@ -33,6 +33,12 @@ def main(argv=None):
                     help="vendor domain of the resources (amd.com/gpu keeps the reference's names; e.g. nvidia.com)")
     ap.add_argument("-plugin_dir", default=v1beta1.DevicePluginPath)
     ap.add_argument("-start_retry_wait", type=float, default=3.0, help="seconds between plugin start attempts")
+    # glog's flags (the reference image runs `-logtostderr=true -stderrthreshold=INFO -v=5`, Dockerfile:33): accepted
+    # and ignored so existing DaemonSet args keep working
+    for g in ("-logtostderr", "-alsologtostderr"):
+        ap.add_argument(g, nargs="?", const="true", default="true", help=argparse.SUPPRESS)
+    for g in ("-stderrthreshold", "-v", "-log_dir", "-vmodule", "-log_backtrace_at"):
+        ap.add_argument(g, default="", help=argparse.SUPPRESS)
     args = ap.parse_args(argv)
     try:
         strategy = ParseStrategy(args.resource_naming_strategy)                                         # main.go:113-117

@@ -47,9 +47,16 @@ bool parse_flags(int argc, char** argv, Flags& f, std::string& err) {
         if (a.empty() || a[0] != '-') { err = "unexpected argument " + a; return false; }
         std::string name = a.substr(1), val;
         const size_t eq = name.find('=');
-        if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); }
+        const std::string bare = eq == std::string::npos ? name : name.substr(0, eq);
+        // glog's flags (the reference's image runs `-logtostderr=true -stderrthreshold=INFO -v=5`, Dockerfile:33) are
+        // accepted and ignored so existing DaemonSet args keep working; this daemon always logs to stderr
+        const bool glog_bool = bare == "logtostderr" || bare == "alsologtostderr";
+        const bool glog_val = bare == "stderrthreshold" || bare == "v" || bare == "log_dir" || bare == "vmodule" || bare == "log_backtrace_at";
+        if (eq != std::string::npos) { val = name.substr(eq + 1); name = bare; }
+        else if (glog_bool) val = "true";  // Go bool flags take no separate argument
         else if (i + 1 < argc) val = argv[++i];
         else { err = "flag needs an argument: -" + name; return false; }
+        if (glog_bool || glog_val) continue;
         if (name == "pulse") f.pulse = atoi(val.c_str());
         else if (name == "resource_naming_strategy") f.strategy = val;
         else if (name == "backend") f.backend = val;
