@@ -306,3 +306,39 @@ def test_native_daemon_soak_streams_come_and_go(daemon_env):
             _, err = proc.communicate()
         kubelet.server.stop(0)
     assert proc.returncode == 0, err[-3000:]
+
+
+def test_native_daemon_mixed_strategy_two_resources(pkg, kfd, tmp_path, short_dir):
+    """-resource_naming_strategy=mixed on a heterogeneous node (main.go:62-89): one socket and one registration
+    per "<compute>_<memory>" resource, each stream carrying only its own devices; `single` refuses such a node."""
+    if not os.path.exists(EXE):
+        import __graft_entry__
+        __graft_entry__.build()
+    V = pkg.v1beta1
+    root = fake_sysfs.build(str(tmp_path / "r"), topo_dir(kfd, "mi308"), compute="cpx", memory="nps1",
+                            hetero_second=("spx", "nps1"))
+    gpus = oamd.GetAMDGPUs(root)
+    r = subprocess.run([EXE, "-resource_naming_strategy=single", "-backend=kfd:" + root, "-plugin_dir", short_dir],
+                       capture_output=True, text=True, timeout=30)
+    assert r.returncode == 1 and "Partitions of different styles" in r.stderr                   # main.go:79
+    kubelet = FakeKubelet(os.path.join(short_dir, "kubelet.sock"), V)
+    proc = subprocess.Popen([EXE, "-resource_naming_strategy=mixed", "-backend=kfd:" + root, "-plugin_dir", short_dir],
+                            stderr=subprocess.PIPE, text=True)
+    try:
+        regs = sorted((kubelet.requests.get(timeout=10) for _ in range(2)), key=lambda q: q.resource_name)
+        assert [q.resource_name for q in regs] == ["amd.com/cpx_nps1", "amd.com/spx_nps1"]
+        assert [q.endpoint for q in regs] == ["amd.com_cpx_nps1", "amd.com_spx_nps1"]
+        for q in regs:
+            res = q.resource_name.split("/")[1]
+            _, want = oplug.list_and_watch_devices(gpus, res)
+            with grpc.insecure_channel("unix://" + os.path.join(short_dir, q.endpoint)) as ch:
+                stream = ch.unary_stream(V.LIST_AND_WATCH, request_serializer=lambda m: m.SerializeToString(),
+                                         response_deserializer=V.ListAndWatchResponse.FromString)(V.Empty())
+                first = next(stream)
+                assert [(d.ID, d.health, d.topology.nodes[0].ID) for d in first.devices] == want and want
+                stream.cancel()
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        _, err = proc.communicate(timeout=10)
+        kubelet.server.stop(0)
+    assert proc.returncode == 0, err[-2000:]
