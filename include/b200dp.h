@@ -133,7 +133,7 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     sysroot=<dir for numa_node lookups, default "/">, p2p_bytes=<default 268435456>,
  *                     busy=probe|skip|shrink (what to do on a GPU another process is using; default probe),
  *                     shrink_bytes=<prefix verified by busy=shrink, default 67108864>, ecc=1 (also fail on new
- *                     uncorrected ECC errors, one NVML query per device per pass), xid=1 (also fail a device
+ *                     uncorrected ECC errors or a failed HBM row remapping, two NVML queries per device per pass), xid=1 (also fail a device
  *                     for good once NVML delivers a critical Xid event for it -- application-level Xids 13, 31,
  *                     43, 45, 68, 109 are ignored; a listener thread waits on the NVML event set and, when a
  *                     device-level Xid arrives, every running b2dp_watch loop of the context sends a heartbeat
@@ -201,7 +201,8 @@ typedef struct b2dp_probe_result {
 } b2dp_probe_result;
 #define B2DP_RES_SKIPPED_BUSY 0x1u /* busy=skip: another process owns the GPU, no pass ran, the last verdict stands */
 #define B2DP_RES_SHRUNK 0x2u       /* busy=shrink: a prefix (shrink_bytes) was verified without re-keying; no GB/s floor */
-#define B2DP_RES_ECC 0x4u          /* ecc=1: NVML reports new uncorrected ECC errors since open => Unhealthy */
+#define B2DP_RES_ECC 0x4u          /* ecc=1: NVML reports new uncorrected ECC errors since open, or a failed HBM row
+                                      remapping (nvmlDeviceGetRemappedRows) => Unhealthy */
 #define B2DP_RES_SMALL_RING 0x10u  /* HBM was short when the context opened (e.g. a restart under running pods): the ring
                                       slots on this GPU are smaller than bytes=; `bytes` reports what a pass moved; no GB/s floor */
 #define B2DP_RES_XID 0x8u          /* xid=1: a critical Xid event was delivered for this device since open (or the

@@ -71,6 +71,7 @@ struct Nvml {
     int (*mig_mode)(void*, unsigned*, unsigned*) = nullptr;
     int (*running_procs)(void*, unsigned*, void*) = nullptr;        // nvmlDeviceGetComputeRunningProcesses_v3
     int (*ecc_total)(void*, int, int, unsigned long long*) = nullptr;  // nvmlDeviceGetTotalEccErrors
+    int (*remapped_rows)(void*, unsigned*, unsigned*, unsigned*, unsigned*) = nullptr;  // nvmlDeviceGetRemappedRows
     struct EventData { void* device; unsigned long long type, data; unsigned gi, ci; };  // nvmlEventData_t
     int (*event_set_create)(void**) = nullptr;
     int (*register_events)(void*, unsigned long long, void*) = nullptr;
@@ -94,6 +95,7 @@ struct Nvml {
         mig_mode = (int (*)(void*, unsigned*, unsigned*))dlsym(lib, "nvmlDeviceGetMigMode");
         running_procs = (int (*)(void*, unsigned*, void*))dlsym(lib, "nvmlDeviceGetComputeRunningProcesses_v3");
         ecc_total = (int (*)(void*, int, int, unsigned long long*))dlsym(lib, "nvmlDeviceGetTotalEccErrors");
+        remapped_rows = (int (*)(void*, unsigned*, unsigned*, unsigned*, unsigned*))dlsym(lib, "nvmlDeviceGetRemappedRows");
         event_set_create = (int (*)(void**))dlsym(lib, "nvmlEventSetCreate");
         register_events = (int (*)(void*, unsigned long long, void*))dlsym(lib, "nvmlDeviceRegisterEvents");
         event_wait = (int (*)(void*, EventData*, unsigned))dlsym(lib, "nvmlEventSetWait_v2");
@@ -723,6 +725,12 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         if (be->cfg.check_ecc && be->gpus[i]->have_ecc) {  // opt-in: an NVML query per device per pass
             unsigned long long now = 0;
             if (be->nvml.ecc_total(be->gpus[i]->nvh, 1, 0, &now) == 0 && now > be->gpus[i]->ecc_base) {
+                o.flags |= B2DP_RES_ECC;
+                o.healthy = 0;
+            }
+            // HBM row remapping: a failed remap means the bad row stays in use (the part is due for replacement)
+            unsigned corr = 0, unc = 0, pending = 0, failed = 0;
+            if (be->nvml.remapped_rows && be->nvml.remapped_rows(be->gpus[i]->nvh, &corr, &unc, &pending, &failed) == 0 && failed) {
                 o.flags |= B2DP_RES_ECC;
                 o.healthy = 0;
             }
