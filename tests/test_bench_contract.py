@@ -34,3 +34,27 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=300, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_product_never_imports_links_or_executes_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+    --impl reference legs may touch it.  The package, its native sources, the tools and the headers must not."""
+    import re
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|#include\s+[\"<][^\">]*oracle/|dlopen\([^)]*oracle|oracle/_build", re.M)
+    offenders = []
+    for top in ("k8s-device-plugin_b200", "tools", "include"):
+        for dirpath, dirnames, files in os.walk(os.path.join(ROOT, top)):
+            dirnames[:] = [d for d in dirnames if d not in ("build", "__pycache__")]
+            for f in files:
+                if not f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h", ".inc")):
+                    continue
+                p = os.path.join(dirpath, f)
+                if pat.search(open(p, errors="replace").read()):
+                    offenders.append(os.path.relpath(p, ROOT))
+    assert offenders == []
+    # bench.py: the oracle appears only inside the CPU-baseline / reference-arm functions
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for m in re.finditer(r"^\s*from oracle import (\w+)", src, re.M):
+        head = src[:m.start()]
+        func = re.findall(r"^def (\w+)\(", head, re.M)[-1]
+        assert func in ("cpu_probe_baseline", "kfd_walk_baseline", "run_reference"), func
