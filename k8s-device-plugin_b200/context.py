@@ -50,6 +50,7 @@ class Context:
             raise N.B2dpError(rc, N.lib.b2dp_last_error(None).decode())
         self._buf = (C.c_uint8 * (1 << 16))()
         self._buf_lock = threading.Lock()      # one response buffer, several gRPC handler threads
+        self._opts_cache = {}
 
     def close(self):
         if self._h:
@@ -141,9 +142,14 @@ class Context:
     def list_and_watch(self, resource: str = "gpu", flags: int = N.LW_INITIAL, external: Optional[Dict[str, bool]] = None,
                        timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0, timed=False):
         """One ListAndWatch send: (serialized ListAndWatchResponse bytes, CycleStats)."""
-        opts = N.CycleOpts()
-        opts.flags = flags
-        opts.probe = N.ProbeOpts(timeout_ms, variant | (N.PROBE_EVENT_TIMING if timed else 0), min_gbs, 0)
+        key = (flags, timeout_ms, variant, min_gbs, timed)
+        opts = self._opts_cache.get(key) if external is None else None      # the heartbeat path re-uses its options block
+        if opts is None:
+            opts = N.CycleOpts()
+            opts.flags = flags
+            opts.probe = N.ProbeOpts(timeout_ms, variant | (N.PROBE_EVENT_TIMING if timed else 0), min_gbs, 0)
+            if external is None:
+                self._opts_cache[key] = opts
         keep = None
         if external is not None:
             opts.flags |= N.LW_EXTERNAL_SOURCE
@@ -164,7 +170,7 @@ class Context:
                 rc = N.lib.b2dp_list_and_watch(self._h, resource.encode(), C.byref(opts), self._buf, len(self._buf),
                                                C.byref(ln), C.byref(st))
             N.check(rc, self._h)
-            wire = bytes(self._buf[:ln.value])
+            wire = C.string_at(self._buf, ln.value)
         del keep
         stats = CycleStats(st.n_devices, st.n_unhealthy, bool(st.homogeneous), bool(st.node_healthy), st.ms_total,
                            st.ms_enumerate, st.ms_probe, st.ms_encode, st.probe_gbs_min, st.probe_gbs_sum,
