@@ -210,9 +210,18 @@ def test_native_daemon_survives_hostile_peers(daemon_env):
         for c in cases:
             shoot(c)
             assert proc.poll() is None, proc.stderr.read()[-3000:]
-        # a POST to a real method with an un-framed body: a clean gRPC error, not a crash
+        # random bytes where a protobuf request belongs: a gRPC status (or an empty answer), never a crash;
         # and the well-behaved kubelet is still served
         with grpc.insecure_channel("unix://" + sock) as ch:
+            for method in (V.ALLOCATE, V.GET_PREFERRED_ALLOCATION, V.PRE_START_CONTAINER):
+                raw = ch.unary_unary(method, request_serializer=lambda b: b, response_deserializer=lambda b: b)
+                for _ in range(60):
+                    blob = bytes(rng.getrandbits(8) for _ in range(rng.randint(0, 48)))
+                    try:
+                        raw(blob, timeout=5)
+                    except grpc.RpcError as e:
+                        assert e.code() in (grpc.StatusCode.INTERNAL, grpc.StatusCode.UNKNOWN), e
+                assert proc.poll() is None
             assert _call(ch, V.GET_OPTIONS, V.Empty(), V.DevicePluginOptions).get_preferred_allocation_available
             stream = ch.unary_stream(V.LIST_AND_WATCH, request_serializer=lambda m: m.SerializeToString(),
                                      response_deserializer=V.ListAndWatchResponse.FromString)(V.Empty())
