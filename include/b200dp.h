@@ -279,8 +279,9 @@ B2DP_API int b2dp_list_and_watch(b2dp_ctx *ctx, const char *resource, const b2dp
  * `l.Heartbeat <- true`) -- until b2dp_watch_stop() (the reference's p.signal).  Each send invokes
  * `cb(user, rc, buf, len, stats)` on that thread with the serialized ListAndWatchResponse (valid
  * during the call); rc != 0 reports a failed cycle.  `opts` as for b2dp_list_and_watch (the
- * INITIAL/HEARTBEAT bits are set by the loop).  b2dp_watch_stop() joins that thread: call it from any thread
- * but the callback's own; b2dp_watch_beat() may be called from anywhere, the callback included.  Stop every
+ * INITIAL/HEARTBEAT bits are set by the loop).  b2dp_watch_stop() joins that thread (called from the callback
+ * itself it only marks the loop to end, and the loop frees the handle on its way out); b2dp_watch_beat() may be
+ * called from anywhere, the callback included.  Stop every
  * watch of a context before b2dp_close(). */
 typedef void (*b2dp_watch_cb)(void *user, int rc, const uint8_t *buf, size_t len, const b2dp_cycle_stats *stats);
 typedef struct b2dp_watch b2dp_watch;

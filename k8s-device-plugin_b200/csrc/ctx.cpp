@@ -450,6 +450,7 @@ struct b2dp_watch {
     std::condition_variable cv;
     int pending_beats = 0;
     bool stop = false;
+    bool self_delete = false;  // stop() was called from the callback: the loop frees the handle on its way out
 };
 
 static void watch_send(b2dp_watch* w, uint32_t flags) {
@@ -481,7 +482,12 @@ static void watch_loop(b2dp_watch* w) {
                     w->pending_beats++;
                 }
             } else w->cv.wait(l, pred);
-            if (w->stop) return;
+            if (w->stop) {
+                const bool del = w->self_delete;
+                l.unlock();
+                if (del) delete w;
+                return;
+            }
             w->pending_beats--;
         }
         watch_send(w, B2DP_LW_HEARTBEAT);
@@ -517,6 +523,11 @@ extern "C" void b2dp_watch_stop(b2dp_watch* w) {
         std::lock_guard<std::mutex> g(w->ctx->mu);
         auto& ws = w->ctx->watches;
         ws.erase(std::remove(ws.begin(), ws.end(), w), ws.end());
+    }
+    if (std::this_thread::get_id() == w->th.get_id()) {  // called from the callback: cannot join ourselves
+        { std::lock_guard<std::mutex> l(w->mu); w->stop = true; w->self_delete = true; }
+        w->th.detach();
+        return;
     }
     { std::lock_guard<std::mutex> l(w->mu); w->stop = true; }
     w->cv.notify_all();

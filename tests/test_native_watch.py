@@ -56,3 +56,26 @@ def test_watch_heterogeneous_resource_without_devices_sends_nothing(pkg, kfd, tm
         w = ctx.watch(lambda rc, wire, st: got.put((rc, st.n_devices)), resource="spx_nps1", flags=pkg._native.LW_NO_PROBE)
         assert got.get(timeout=5) == (0, 16)
         w.stop()
+
+
+def test_watch_can_be_stopped_from_its_own_callback(pkg, tmp_path):
+    """b2dp_watch_stop() called on the loop's own thread (from the callback) must not try to join itself:
+    the loop ends after the current send and frees the handle."""
+    root = str(tmp_path / "t")
+    pkg.synth.write_b200_tree(root, n_gpus=2)
+    got = queue.Queue()
+    holder = {}
+    with pkg.Context("kfd:" + root) as ctx:
+        sends = [0]
+
+        def cb(rc, wire, st):
+            sends[0] += 1
+            got.put(len(wire))
+            if sends[0] == 2:
+                while "w" not in holder:                    # ctx.watch() may not have returned yet
+                    time.sleep(0.001)
+                holder["w"].stop()                          # second send: stop from inside
+        holder["w"] = ctx.watch(cb, pulse_ms=20, flags=pkg._native.LW_NO_PROBE)
+        assert got.get(timeout=5) > 0 and got.get(timeout=5) > 0
+        time.sleep(0.3)
+        assert got.empty()                                  # no third send: the loop is gone
