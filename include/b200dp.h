@@ -125,6 +125,9 @@ typedef struct b2dp_ctx b2dp_ctx;
 /* backend_uri:
  *   "kfd:<sysroot>"   parity mode: <sysroot> plays "/" and holds sys/module/amdgpu/drivers,
  *                     sys/class/kfd/kfd/topology, sys/devices/platform/amdgpu_xcp_*; no GPU work.
+ *   "synthetic:<N>[,mig=<k>][,compute=<name>][,memory=<name>][,cpus=<c>]"
+ *                     a generated kfd-shaped tree of an N x B200 NVSwitch node (k partitions per GPU for the
+ *                     MIG/CPX-style layout), opened through the kfd: reader and removed at close; CPU only.
  *   "cuda:[k=v,...]"  real B200s.  keys: devices=0+1+2 (default all), bytes=<S per buffer,
  *                     default 1073741824>, slots=<buffers in the probe ring, default 2 = ping-pong; with M
  *                     slots pass k verifies slot k mod M (written by pass k-1) and re-keys it into slot

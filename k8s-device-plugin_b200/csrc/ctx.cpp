@@ -41,6 +41,7 @@ struct b2dp_ctx {
     std::vector<float> p2p_gbs; // last matrix, n x n
     std::vector<Device> stream_devs;  // the device list of the current ListAndWatch stream
     bool have_stream_devs = false;
+    std::string owned_tmp_root;       // synthetic: backend -- the generated tree, removed at close
     std::vector<b2dp_watch*> watches;  // running b2dp_watch loops (guarded by mu): a latched Xid beats them all at once
 };
 
@@ -88,6 +89,12 @@ extern "C" const char* b2dp_strerror(int code) {
 extern "C" int b2dp_abi_version(void) { return B2DP_ABI_VERSION; }
 
 // ---- open / close ------------------------------------------------------------------------
+static bool mkdirs(const std::string& p);
+static bool write_file(const std::string& path, const std::string& data);
+static bool write_synthetic_tree(const std::string& root, int n_gpus, int partitions, int n_cpu_nodes,
+                                 const std::string& compute, const std::string& memory);
+static void remove_tree(const std::string& root);
+
 static bool parse_kv(const std::string& body, std::map<std::string, std::string>& kv) {
     size_t pos = 0;
     while (pos < body.size()) {
@@ -116,6 +123,39 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             delete c;
             return fail(B2DP_E_NODRIVER, "amdgpu driver unavailable under " + u.substr(4));
         }
+        *out = c;
+        return B2DP_OK;
+    }
+    if (u.compare(0, 10, "synthetic:") == 0) {
+        // "synthetic:<N>[,mig=<k>][,compute=<name>][,memory=<name>][,cpus=<c>]": a generated kfd-shaped tree of an
+        // N x B200 NVSwitch node (every pair linked with type 11, GPUs split over two NUMA nodes, optionally k
+        // partitions per GPU, the MIG/CPX-style layout) opened through the kfd: reader -- CPU only, no probe.
+        std::string body = u.substr(10);
+        const size_t comma = body.find(',');
+        const int n_gpus = atoi(body.substr(0, comma).c_str());
+        std::map<std::string, std::string> kv;
+        if (comma != std::string::npos && !parse_kv(body.substr(comma + 1), kv)) return fail(B2DP_E_INVAL, "bad synthetic: uri");
+        int mig = 1, cpus = 2;
+        std::string compute, memory;
+        for (auto& p : kv) {
+            if (p.first == "mig") mig = atoi(p.second.c_str());
+            else if (p.first == "compute") compute = p.second;
+            else if (p.first == "memory") memory = p.second;
+            else if (p.first == "cpus") cpus = atoi(p.second.c_str());
+            else return fail(B2DP_E_INVAL, "unknown synthetic: option " + p.first);
+        }
+        if (n_gpus < 1 || n_gpus > 64 || mig < 1 || mig > 8 || cpus < 0 || cpus > 16) return fail(B2DP_E_INVAL, "synthetic: wants 1..64 GPUs, mig 1..8");
+        // partitions are only listed when their parent GPU reports BOTH partition types (amdgpu.go:240-249)
+        if (mig > 1 && compute.empty()) compute = "mig" + std::to_string(mig);
+        if (mig > 1 && memory.empty()) memory = "nps1";
+        char tmpl[64];
+        snprintf(tmpl, sizeof tmpl, "%s/b2dp_syn_XXXXXX", go::is_dir("/dev/shm") ? "/dev/shm" : "/tmp");
+        if (!mkdtemp(tmpl)) return fail(B2DP_E_IO, std::string("mkdtemp: ") + strerror(errno));
+        if (!write_synthetic_tree(tmpl, n_gpus, mig, cpus, compute, memory)) { remove_tree(tmpl); return fail(B2DP_E_IO, "writing the synthetic tree failed"); }
+        auto* c = new b2dp_ctx();
+        c->kind = b2dp_ctx::KFD;
+        c->sysroot = tmpl;
+        c->owned_tmp_root = tmpl;
         *out = c;
         return B2DP_OK;
     }
@@ -175,12 +215,13 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         *out = c;
         return B2DP_OK;
     }
-    return fail(B2DP_E_INVAL, "unknown backend uri (want kfd:<sysroot> or cuda:[opts])");
+    return fail(B2DP_E_INVAL, "unknown backend uri (want kfd:<sysroot>, synthetic:<N>[,mig=<k>] or cuda:[opts])");
 }
 
 extern "C" void b2dp_close(b2dp_ctx* c) {
     if (!c) return;
     if (c->cuda) cuda_backend_close(c->cuda);
+    if (!c->owned_tmp_root.empty()) remove_tree(c->owned_tmp_root);
     delete c;
 }
 
@@ -755,6 +796,96 @@ static bool write_file(const std::string& path, const std::string& data) {
     bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
     fclose(f);
     return ok;
+}
+
+static std::string link_props(int type, int from, int to, int weight) {
+    char lp[512];
+    snprintf(lp, sizeof lp,
+             "type %d\nversion_major 0\nversion_minor 0\nnode_from %d\nnode_to %d\nweight %d\nmin_latency 0\n"
+             "max_latency 0\nmin_bandwidth 0\nmax_bandwidth 0\nrecommended_transfer_size 0\nflags 1\n",
+             type, from, to, weight);
+    return lp;
+}
+
+// The node shape of k8s-device-plugin_b200/synth.py:write_b200_tree, file for file (tests compare the two).
+static bool write_synthetic_tree(const std::string& root, int n_gpus, int partitions, int n_cpu_nodes,
+                                 const std::string& compute, const std::string& memory) {
+    const long long vram_bytes = 192265846784LL;
+    const int sm_count = 148;
+    auto upper = [](std::string v) { for (auto& ch : v) ch = (char)toupper((unsigned char)ch); return v; };
+    const std::string nodes = root + "/sys/class/kfd/kfd/topology/nodes";
+    bool ok = mkdirs(root + "/sys/devices/platform");
+    for (int k = 0; k < n_cpu_nodes; ++k) {
+        char props[512];
+        snprintf(props, sizeof props,
+                 "cpu_cores_count 64\nsimd_count 0\nmem_banks_count 1\ncaches_count 0\nio_links_count 0\n"
+                 "cpu_core_id_base %d\nsimd_id_base 0\nvendor_id 0\ndevice_id 0\nlocation_id 0\ndomain 0\n"
+                 "drm_render_minor 0\n", k * 64);
+        ok &= write_file(nodes + "/" + std::to_string(k) + "/properties", props);
+    }
+    std::vector<std::pair<int, int>> gpu_nodes;  // (node id, gpu index)
+    int node_id = n_cpu_nodes, minor = 128, card = 0;
+    for (int g = 0; g < n_gpus; ++g) {
+        const int bus = 0x19 + 0x10 * g;
+        char bdf[32];
+        snprintf(bdf, sizeof bdf, "0000:%02x:00.0", bus);
+        const int numa = g < (n_gpus + 1) / 2 ? 0 : 1;
+        const std::string pci = root + "/sys/module/amdgpu/drivers/pci:amdgpu/" + bdf;
+        ok &= write_file(pci + "/numa_node", std::to_string(numa) + "\n");
+        if (!compute.empty()) {
+            ok &= write_file(pci + "/current_compute_partition", upper(compute) + "\n");
+            ok &= write_file(pci + "/available_compute_partition", "SPX, " + upper(compute) + "\n");
+        }
+        if (!memory.empty()) {
+            ok &= write_file(pci + "/current_memory_partition", upper(memory) + "\n");
+            ok &= write_file(pci + "/available_memory_partition", upper(memory) + "\n");
+        }
+        for (int p = 0; p < partitions; ++p) {
+            const std::string base = p == 0 ? pci : root + "/sys/devices/platform/amdgpu_xcp_" + std::to_string(g * 8 + p);
+            ok &= mkdirs(base + "/drm/card" + std::to_string(card));
+            ok &= mkdirs(base + "/drm/renderD" + std::to_string(minor));
+            const std::string drm = root + "/sys/class/drm/card" + std::to_string(card) + "/device";
+            ok &= write_file(drm + "/device", "0x2901\n");
+            ok &= write_file(drm + "/product_name", "NVIDIA B200\n");
+            ok &= write_file(drm + "/driver/module/version", "580.159.03\n");
+            ok &= write_file(drm + "/driver/module/srcversion", "SYNTHETIC0000000000000000\n");
+            char props[1024];
+            snprintf(props, sizeof props,
+                     "cpu_cores_count 0\nsimd_count %d\nmem_banks_count 1\ncaches_count 0\nio_links_count %d\n"
+                     "cpu_core_id_base 0\nsimd_id_base 0\nmax_waves_per_simd 16\nwave_front_size 32\nsimd_per_cu 4\n"
+                     "gfx_target_version 100000\nvendor_id 4318\ndevice_id 10497\nlocation_id %d\ndomain 0\n"
+                     "drm_render_minor %d\nlocal_mem_size %lld\n",
+                     sm_count * 4 / partitions, n_gpus * partitions - 1, bus << 8, minor, vram_bytes / partitions);
+            const std::string nd = nodes + "/" + std::to_string(node_id);
+            ok &= write_file(nd + "/properties", props);
+            char mb[256];
+            snprintf(mb, sizeof mb, "heap_type 1\nsize_in_bytes %lld\nflags 0\nwidth 8192\nmem_clk_max 3996\n", vram_bytes / partitions);
+            ok &= write_file(nd + "/mem_banks/0/properties", mb);
+            gpu_nodes.push_back({node_id, g});
+            ++node_id; ++minor; ++card;
+        }
+    }
+    for (auto& a : gpu_nodes) {
+        int li = 0;
+        for (auto& b : gpu_nodes) {
+            if (b.first == a.first) continue;
+            ok &= write_file(nodes + "/" + std::to_string(a.first) + "/io_links/" + std::to_string(li++) + "/properties",
+                             link_props(11, a.first, b.first, b.second == a.second ? 13 : 15));
+        }
+    }
+    return ok;
+}
+
+static void remove_tree(const std::string& root) {
+    std::vector<std::string> names;
+    if (go::list_dir_sorted(root, names))
+        for (auto& n : names) {
+            const std::string p = root + "/" + n;
+            struct stat st;
+            if (::lstat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) remove_tree(p);
+            else ::unlink(p.c_str());
+        }
+    ::rmdir(root.c_str());
 }
 
 extern "C" int b2dp_export_kfd_tree(b2dp_ctx* c, const char* dir_c) {

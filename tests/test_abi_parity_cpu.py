@@ -492,3 +492,40 @@ def test_vendor_domain_is_configurable(P):
     finally:
         P.labeller.setVendorDomain("amd.com")
     assert P.labeller.createLabelPrefix("vram", True) == "beta.amd.com/gpu.vram"
+
+
+@pytest.mark.parametrize("n,mig", [(1, 1), (8, 1), (8, 7), (3, 2)])
+def test_synthetic_backend_equals_the_written_tree(P, tmp_path, n, mig):
+    """`synthetic:<N>[,mig=<k>]` (BASELINE config 5 ii) generates the same node shape as synth.write_b200_tree:
+    device table, resource names, ListAndWatch list, pair weights, allocations and labels equal the kfd: backend
+    on the written tree and the reference algorithm (oracle) on it; the generated tree is removed at close."""
+    import glob
+    root = str(tmp_path / "t")
+    comp, mem = ("mig%d" % mig, "nps1") if mig > 1 else ("", "")
+    ids = P.synth.write_b200_tree(root, n_gpus=n, partitions=mig, compute_partition=comp, memory_partition=mem)
+    before = set(glob.glob("/dev/shm/b2dp_syn_*") + glob.glob("/tmp/b2dp_syn_*"))
+    with P.Context("synthetic:%d,mig=%d" % (n, mig)) as syn, P.Context("kfd:" + root) as ref:
+        made = set(glob.glob("/dev/shm/b2dp_syn_*") + glob.glob("/tmp/b2dp_syn_*")) - before
+        assert len(made) == 1
+        want = oamd.GetAMDGPUs(root)
+        assert syn.enumerate() == ref.enumerate() == want and sorted(want) == ids
+        assert syn.resource_list("mixed") == ref.resource_list("mixed") == oplug.getResourceList("mixed", root)[0]
+        res = syn.resource_list("single")[0]
+        assert syn.list_and_watch(res, P._native.LW_INITIAL)[0] == ref.list_and_watch(res, P._native.LW_INITIAL)[0]
+        assert syn.node_health() == ref.node_health() is True
+        assert syn.start() == ref.start() == (0 if len(ids) > 1 else P._native.E_ALLOC_NO_WEIGHTS)
+        if len(ids) > 1:
+            opol = oalloc.BestEffortPolicy()
+            assert opol.Init(oplug.getDevices(root), root + "/sys/class/kfd/kfd/topology/nodes") is None
+            for size in sorted({1, 2, min(len(ids), 7), len(ids)}):
+                got = syn.preferred_allocation(ids, [], size)
+                assert got == ref.preferred_allocation(ids, [], size) == opol.Allocate(list(ids), [], size)[0]
+        gens = P.labeller.labelGeneratorNames()
+        assert syn.generate_labels(gens) == ref.generate_labels(gens) == olab.generateLabels({g: True for g in gens}, root)
+        with pytest.raises(P._native.B2dpError) as ei:
+            syn.probe_health()
+        assert ei.value.code == P._native.E_UNSUPPORTED          # CPU only: no probe, no fallback
+    assert not (set(glob.glob("/dev/shm/b2dp_syn_*") + glob.glob("/tmp/b2dp_syn_*")) - before)
+    for bad in ("synthetic:0", "synthetic:8,mig=9", "synthetic:8,frob=1", "synthetic:abc"):
+        with pytest.raises(P._native.B2dpError):
+            P.Context(bad)
