@@ -268,7 +268,18 @@ static int cmd_sweep(int argc, char** argv) {
         }
         b2dp_close(c);
     }
+    for (const char* uri : {"synthetic:8,mig=7", "synthetic:1", "synthetic:16,mig=2,compute=cpx,memory=nps4"}) {
+        b2dp_ctx* sc = nullptr;
+        EXPECT(b2dp_open(uri, &sc) == B2DP_OK && sc);
+        if (!sc) continue;
+        (void)ctx_pass(sc, false);
+        const uint64_t h1 = ctx_pass(sc, true), h2 = ctx_pass(sc, true);
+        EXPECT(h1 == h2);
+        digest ^= h1;
+        b2dp_close(sc);  // removes the generated tree
+    }
     b2dp_ctx* c = nullptr;
+    EXPECT(b2dp_open("synthetic:0", &c) == B2DP_E_INVAL && c == nullptr);
     EXPECT(b2dp_open("bogus:", &c) == B2DP_E_INVAL);
     EXPECT(b2dp_open("cuda:", &c) == B2DP_E_NOGPU);      // stubbed in this build
     EXPECT(b2dp_open("cuda:slots=1", &c) == B2DP_E_INVAL);
