@@ -297,6 +297,32 @@ def main():
     barrier()
     t_value = max_over_ranks(t_value)
 
+    # ---- context for the roofline: the driver's own device-to-device copy of the same size, in this run, on this
+    # GPU, timed the same way (CUDA events, after warm-up) -- what a plain copy achieves on this part today -------
+    drv_copy_gbs = None
+    try:
+        a_t = torch.empty(S_BYTES, dtype=torch.uint8, device="cuda")
+        b_t = torch.empty(S_BYTES, dtype=torch.uint8, device="cuda")
+        a_t.zero_()
+        for _ in range(5):
+            b_t.copy_(a_t)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(20):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            b_t.copy_(a_t)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        drv_copy_gbs = 2.0 * S_BYTES / (best * 1e-3) / 1e9
+        del a_t, b_t
+        torch.cuda.empty_cache()
+    except Exception as e:      # noqa: BLE001
+        print("driver copy reference skipped: %r" % (e,), file=sys.stderr)
+    barrier()
+
     # ---- e2e leg: the kubelet-facing call ----------------------------------------------------------
     warm(lambda: ctx.list_and_watch("gpu", N.LW_HEARTBEAT, variant=args.variant))
     barrier()
@@ -403,7 +429,9 @@ def main():
         "unhealthy_verdicts": int(unhealthy),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic_per_launch(), "peak_source": peak_src,
-                     "kernel_ms_mean": round(kernel_ms_mean, 5), "kernel_ms_mean_slowest_rank": round(kernel_ms_max_rank, 5)},
+                     "kernel_ms_mean": round(kernel_ms_mean, 5), "kernel_ms_mean_slowest_rank": round(kernel_ms_max_rank, 5),
+                     "driver_d2d_copy_gbs_same_run": None if drv_copy_gbs is None else round(drv_copy_gbs, 1),
+                     "note": "driver_d2d_copy = torch copy_ of the same 1 GiB (best of 20, CUDA events): the mixed read+write ceiling of this part; the probe verifies and re-keys every word at that rate"},
         "clocks": clocks,
     }
     # the reference's own sysfs/kfd CPU path on this box's host cores, in the same run, at every N
