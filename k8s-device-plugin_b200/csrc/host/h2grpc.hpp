@@ -519,6 +519,7 @@ public:
 
 private:
     struct Req { Headers headers; std::string block, body; bool headers_done = false; std::shared_ptr<ServerStream> stream; };
+    static constexpr size_t kMaxOpenRequests = 256, kMaxHeaderBlock = 64 * 1024, kMaxMessageBytes = 4 * 1024 * 1024;
     struct Peer { std::shared_ptr<Conn> conn; std::thread th; std::atomic<bool> done{false}; };
 
     void accept_loop() {
@@ -573,11 +574,13 @@ private:
             switch (f.type) {
             case F_HEADERS: case F_CONTINUATION: {
                 if (f.stream == 0) { ok = false; break; }
+                if (reqs.size() >= kMaxOpenRequests && !reqs.count(f.stream)) { ok = false; break; }  // a peer hoarding streams
                 Req& r = reqs[f.stream];
                 std::string frag;
                 if (f.type == F_HEADERS) { if (!Conn::strip(f, frag)) { ok = false; break; } }
                 else frag = f.payload;
                 r.block += frag;
+                if (r.block.size() > kMaxHeaderBlock) { ok = false; break; }
                 const bool end_stream = f.type == F_HEADERS && (f.flags & FL_END_STREAM);
                 if (f.flags & FL_END_HEADERS) {
                     continuing = 0;
@@ -593,7 +596,10 @@ private:
                 std::string body;
                 if (!Conn::strip(f, body)) { ok = false; break; }
                 const bool end = f.flags & FL_END_STREAM;
-                if (it != reqs.end()) it->second.body += body;
+                if (it != reqs.end()) {
+                    it->second.body += body;
+                    if (it->second.body.size() > kMaxMessageBytes) { ok = false; break; }  // gRPC's default receive limit
+                }
                 ok = c->replenish(f.stream, f.payload.size(), it != reqs.end() && !end);
                 if (ok && end && it != reqs.end()) dispatch(c, f.stream, reqs, open_streams, qmu, qcv, q);
                 break;

@@ -201,6 +201,8 @@ def test_native_daemon_survives_hostile_peers(daemon_env):
             PREFACE + hdr_ok + frame(1, 0x5 | 0x8, 1, b"\xf0" + b"\x82"),       # pad length larger than the payload
             PREFACE + hdr_ok + frame(1, 0x5, 1, b"\x83\x86\x44\x01/") + frame(3, 0, 1, b"\x00\x00\x00\x08"),  # GET + RST
         ]
+        cases.append(PREFACE + hdr_ok + b"".join(frame(1, 0x4, 1 + 2 * i, b"\x83\x86\x44\x01/") for i in range(400)))  # 400 streams never closed
+        cases.append(PREFACE + hdr_ok + frame(1, 0x0, 1, b"\x00\x01a\x01b") + frame(9, 0x0, 1, b"\x00\x01a\x01b" * 3000) * 8)  # endless CONTINUATION
         for _ in range(40):                                                     # random frame soup
             blob = PREFACE + hdr_ok
             for _ in range(rng.randint(1, 12)):
