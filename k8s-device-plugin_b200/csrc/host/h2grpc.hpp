@@ -519,6 +519,7 @@ public:
 
 private:
     struct Req { Headers headers; std::string block, body; bool headers_done = false; std::shared_ptr<ServerStream> stream; };
+    static constexpr size_t kMaxConnections = 64;
     static constexpr size_t kMaxOpenRequests = 256, kMaxHeaderBlock = 64 * 1024, kMaxMessageBytes = 4 * 1024 * 1024;
     struct Peer { std::shared_ptr<Conn> conn; std::thread th; std::atomic<bool> done{false}; };
 
@@ -535,6 +536,7 @@ private:
                     if ((*it)->done.load()) { if ((*it)->th.joinable()) (*it)->th.join(); it = peers_.erase(it); }
                     else ++it;
                 }
+                if (peers_.size() >= kMaxConnections) { p->conn->close_fd(); continue; }  // the kubelet needs one
                 peers_.push_back(p);
                 p->th = std::thread([this, p] { serve(p->conn); p->done = true; });
             }
