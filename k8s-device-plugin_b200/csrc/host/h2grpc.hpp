@@ -737,4 +737,88 @@ inline Status unary_call_unix(const std::string& sock_path, const std::string& m
     return st;
 }
 
+// ---- client: a server-streaming call (what the kubelet does with ListAndWatch); single-threaded reader -----------
+class ClientStream {
+public:
+    ~ClientStream() { close(); }
+    Status open(const std::string& sock_path, const std::string& method_path, const std::string& request, int timeout_ms = 5000) {
+        struct sockaddr_un a{};
+        if (sock_path.size() >= sizeof a.sun_path) return {GRPC_UNAVAILABLE, "socket path too long"};
+        const int fd = ::socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+        if (fd < 0) return {GRPC_UNAVAILABLE, std::string("socket: ") + strerror(errno)};
+        a.sun_family = AF_UNIX;
+        memcpy(a.sun_path, sock_path.c_str(), sock_path.size() + 1);
+        if (::connect(fd, (struct sockaddr*)&a, sizeof a) != 0) {
+            const std::string e = std::string("connect ") + sock_path + ": " + strerror(errno);
+            ::close(fd);
+            return {GRPC_UNAVAILABLE, e};
+        }
+        conn_ = std::make_unique<Conn>(fd);
+        if (!conn_->write_preface() || !conn_->write_frame(F_SETTINGS, 0, 0, "") ||
+            !conn_->send_headers(sid_, {{":method", "POST"}, {":scheme", "http"}, {":path", method_path}, {":authority", "localhost"},
+                                        {"content-type", "application/grpc"}, {"te", "trailers"}}, false) ||
+            !conn_->send_data(sid_, grpc_frame(request), true, timeout_ms))
+            return {GRPC_UNAVAILABLE, "write failed"};
+        return Status{};
+    }
+    // Next message of the stream.  false: the stream ended (status() says how) or timed out.
+    bool next(std::string& msg, int timeout_ms) {
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
+        for (;;) {
+            if (pop(msg)) return true;
+            if (ended_ || !conn_) return false;
+            const auto left = std::chrono::duration_cast<std::chrono::milliseconds>(deadline - std::chrono::steady_clock::now()).count();
+            Frame f;
+            if (left <= 0 || !conn_->read_frame(f, (int)left)) { if (left > 0) { ended_ = true; status_ = {GRPC_UNAVAILABLE, "connection closed"}; } return false; }
+            if ((f.type == F_HEADERS || f.type == F_CONTINUATION) && f.stream == sid_) {
+                std::string frag;
+                if (f.type == F_HEADERS) { if (!Conn::strip(f, frag)) return fail("bad HEADERS"); }
+                else frag = f.payload;
+                block_ += frag;
+                if (f.flags & FL_END_HEADERS) {
+                    if (!conn_->hpack.decode((const uint8_t*)block_.data(), block_.size(), headers_)) return fail("HPACK error");
+                    block_.clear();
+                }
+                if (f.type == F_HEADERS && (f.flags & FL_END_STREAM)) {
+                    ended_ = true;
+                    const std::string gs = find_header(headers_, "grpc-status");
+                    status_ = {gs.empty() ? GRPC_UNKNOWN : atoi(gs.c_str()), percent_decode(find_header(headers_, "grpc-message"))};
+                }
+            } else if (f.type == F_DATA && f.stream == sid_) {
+                std::string d;
+                if (!Conn::strip(f, d)) return fail("bad DATA");
+                body_ += d;
+                conn_->replenish(sid_, f.payload.size(), !(f.flags & FL_END_STREAM));
+                if (f.flags & FL_END_STREAM) { ended_ = true; status_ = {GRPC_UNKNOWN, "stream ended without trailers"}; }
+            } else if (f.type == F_RST_STREAM && f.stream == sid_) { ended_ = true; status_ = {GRPC_UNAVAILABLE, "stream reset"}; }
+            else if (f.type == F_GOAWAY) { ended_ = true; status_ = {GRPC_UNAVAILABLE, "GOAWAY"}; }
+            else if (!conn_->handle_control(f)) return fail("HTTP/2 protocol error");
+        }
+    }
+    void close() {
+        if (conn_) {
+            if (!ended_) conn_->write_frame(F_RST_STREAM, 0, sid_, std::string("\x00\x00\x00\x08", 4));  // CANCEL
+            conn_.reset();
+        }
+    }
+    const Status& status() const { return status_; }
+
+private:
+    bool pop(std::string& msg) {
+        if (body_.size() < 5 || body_[0] != 0) return false;
+        const uint32_t n = ((uint32_t)(uint8_t)body_[1] << 24) | ((uint32_t)(uint8_t)body_[2] << 16) | ((uint32_t)(uint8_t)body_[3] << 8) | (uint32_t)(uint8_t)body_[4];
+        if (body_.size() - 5 < n) return false;
+        msg.assign(body_, 5, n);
+        body_.erase(0, 5 + (size_t)n);
+        return true;
+    }
+    bool fail(const char* why) { ended_ = true; status_ = {GRPC_INTERNAL, why}; return false; }
+    std::unique_ptr<Conn> conn_;
+    const uint32_t sid_ = 1;
+    std::string block_, body_;
+    Headers headers_;
+    bool ended_ = false;
+    Status status_;
+};
+
 }  // namespace h2

@@ -353,3 +353,18 @@ def test_native_daemon_mixed_strategy_two_resources(pkg, kfd, tmp_path, short_di
         _, err = proc.communicate(timeout=10)
         kubelet.server.stop(0)
     assert proc.returncode == 0, err[-2000:]
+
+
+def test_native_kubelet_sim_drives_the_native_daemon():
+    """tools/b200dp_kubelet_sim: the kubelet's side (Registration server + ListAndWatch streaming client) on the
+    same native gRPC, against the daemon on a generated 8-GPU node -- native to native, no Python on either side."""
+    import json
+    sim = os.path.join(ROOT, "tools", "b200dp_kubelet_sim")
+    if not (os.path.exists(sim) and os.path.exists(EXE)):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([sim, EXE, "synthetic:8,mig=7", "100"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr[-2000:])
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["resource"] == "amd.com/gpu" and d["iterations"] == 100 and d["response_bytes"] > 56 * 20
+    assert 0 < d["heartbeat_to_kubelet_ms_median"] < 50
