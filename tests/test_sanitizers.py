@@ -28,11 +28,25 @@ SOURCES = [os.path.join(CSRC, f) for f in ("kfd.cpp", "allocator.cpp", "labels.c
     os.path.join(HERE, "native", "cuda_stub.cpp"), os.path.join(HERE, "native", "abi_stress.cpp")]
 
 
-def _build(out, flags):
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-omit-frame-pointer", "-Wall", "-Werror"] + flags + SOURCES + \
-          ["-o", out, "-lpthread", "-ldl"]
+CACHE = os.path.join(HERE, "native", "_build")          # git-ignored; binaries are re-used while no source is newer
+HEADERS = [os.path.join(ROOT, "include", "b200dp.h")] + [os.path.join(CSRC, f) for f in
+           ("gosem.hpp", "internal.hpp", "pbwire.hpp", "hpack_huffman.inc", "host/h2grpc.hpp", "host/pbread.hpp")]
+
+
+def _fresh(out, sources):
+    return os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in list(sources) + HEADERS)
+
+
+def _build(out, flags, sources=None, werror=True):
+    sources = sources or SOURCES
+    if _fresh(out, sources):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-omit-frame-pointer", "-Wall"] + (["-Werror"] if werror else []) + \
+          flags + list(sources) + ["-o", out + ".tmp", "-lpthread", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
+    os.replace(out + ".tmp", out)
     return out
 
 
@@ -46,8 +60,8 @@ def bins(tmp_path_factory):
     if probe.returncode != 0:
         pytest.skip("sanitizer runtimes not installed: " + probe.stderr[-200:])
     return {
-        "asan": _build(str(d / "abi_asan"), ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]),
-        "tsan": _build(str(d / "abi_tsan"), ["-fsanitize=thread"]),
+        "asan": _build(os.path.join(CACHE, "abi_asan"), ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]),
+        "tsan": _build(os.path.join(CACHE, "abi_tsan"), ["-fsanitize=thread"]),
     }
 
 
@@ -109,13 +123,12 @@ def test_native_daemon_under_sanitizers(san, tmp_path):
     the daemon exit non-zero, which those tests check."""
     if shutil.which("g++") is None:
         pytest.skip("no g++")
-    exe = str(tmp_path / "plugind_san")
-    srcs = SOURCES[:-1] + [os.path.join(CSRC, "host", "plugind.cpp")]
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=" + san] + srcs +
-                       ["-o", exe, "-lpthread", "-ldl"], capture_output=True, text=True)
-    if r.returncode != 0 and "sanitize" in r.stderr:
+    probe = subprocess.run(["g++", "-fsanitize=" + san, "-x", "c++", "-", "-o", str(tmp_path / "probe")],
+                           input="int main(){return 0;}", capture_output=True, text=True)
+    if probe.returncode != 0:
         pytest.skip("sanitizer runtimes not installed")
-    assert r.returncode == 0, r.stderr[-4000:]
+    srcs = SOURCES[:-1] + [os.path.join(CSRC, "host", "plugind.cpp")]
+    exe = _build(os.path.join(CACHE, "plugind_" + san.replace(",", "_")), ["-fsanitize=" + san], srcs, werror=False)
     env = _env()
     env["B200DP_PLUGIND"] = exe
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_native_plugind.py"), "-x", "-q",
