@@ -37,6 +37,7 @@ struct Flags {
     double start_retry_wait = 3.0;                   // dpm/manager.go:19
     int link_check = 0;
     std::string exporter_socket;                     // optional: serve metricssvc.MetricsService here (health.go:36)
+    bool version = false;
 };
 
 // Go's flag package: -name=value, -name value, --name...; bools not needed here
@@ -44,6 +45,7 @@ bool parse_flags(int argc, char** argv, Flags& f, std::string& err) {
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a.rfind("--", 0) == 0) a = a.substr(1);
+        if (a == "-version") { f.version = true; continue; }
         if (a.empty() || a[0] != '-') { err = "unexpected argument " + a; return false; }
         std::string name = a.substr(1), val;
         const size_t eq = name.find('=');
@@ -339,6 +341,10 @@ int main(int argc, char** argv) {
     Flags fl;
     std::string err;
     if (!parse_flags(argc, argv, fl, err)) { logf("%s", err.c_str()); return 2; }
+    if (fl.version) {  // the reference stamps main.gitDescribe at link time (Makefile -X main.gitDescribe)
+        printf("b200dp_plugind: libb200dp ABI %d (header %d), built %s\n", b2dp_abi_version(), B2DP_ABI_VERSION, __DATE__);
+        return 0;
+    }
     if (fl.strategy != "single" && fl.strategy != "mixed") {  // main.go:42-51,113-117
         logf("invalid resource naming strategy: %s", fl.strategy.c_str());
         return 1;

@@ -134,6 +134,8 @@ def test_native_daemon_flag_and_start_errors(daemon_env):
     r = subprocess.run([EXE, "-logtostderr=true", "-stderrthreshold=INFO", "-v=5", "-logtostderr", "-resource_naming_strategy=bogus"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "invalid resource naming strategy: bogus" in r.stderr
+    r = subprocess.run([EXE, "-version"], capture_output=True, text=True)
+    assert r.returncode == 0 and "libb200dp ABI 2" in r.stdout
     r = subprocess.run([EXE, "-no_such_flag=1"], capture_output=True, text=True)
     assert r.returncode == 2 and "flag provided but not defined: -no_such_flag" in r.stderr
     r = subprocess.run([EXE, "-backend=kfd:" + root + "/nope"], capture_output=True, text=True)
