@@ -141,6 +141,7 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     43, 45, 68, 109 are ignored; a listener thread waits on the NVML event set and, when a
  *                     device-level Xid arrives, every running b2dp_watch loop of the context sends a heartbeat
  *                     cycle at once instead of at its next pulse).
+ *                     cdi=<kind> (e.g. cdi=nvidia.com/gpu): Allocate also returns cdi_devices "<kind>=<minor>".
  *                     A GPU whose own setup fails (or that break=<i>+<j>, a test hook, names by enumeration index)
  *                     stays in the device list and is reported Unhealthy with B2DP_E_CUDA on every pass; the open
  *                     only fails when no GPU could be set up.
@@ -300,8 +301,8 @@ B2DP_API void b2dp_watch_stop(b2dp_watch *w);
  * cuda backend: /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools, then /dev/nvidia<minor>. */
 B2DP_API int b2dp_device_specs(b2dp_ctx *ctx, const char *const *ids, int n_ids, b2dp_devspec *out, int cap, int *n);
 /* Same, serialized as v1beta1.ContainerAllocateResponse (api.proto: devices=3).  The cuda backend also sets
- * envs["NVIDIA_VISIBLE_DEVICES"] = the allocated /dev/nvidia minors ("void" if none); the kfd backend sets
- * no envs, like the reference. */
+ * envs["NVIDIA_VISIBLE_DEVICES"] = the allocated /dev/nvidia minors ("void" if none) and, with the cdi=<kind> URI
+ * option, cdi_devices (field 5) "<kind>=<minor>"; the kfd backend sets neither, like the reference. */
 B2DP_API int b2dp_allocate_response(b2dp_ctx *ctx, const char *const *ids, int n_ids, uint8_t *buf, size_t cap, size_t *len);
 
 /* ---- allocator (internal/pkg/allocator) ------------------------------------------ */

@@ -41,6 +41,7 @@ struct b2dp_ctx {
     std::vector<float> p2p_gbs; // last matrix, n x n
     std::vector<Device> stream_devs;  // the device list of the current ListAndWatch stream
     bool have_stream_devs = false;
+    std::string cdi_kind;             // cuda: optional CDI kind ("nvidia.com/gpu"): Allocate also names CDI devices
     std::string owned_tmp_root;       // synthetic: backend -- the generated tree, removed at close
     std::vector<b2dp_watch*> watches;  // running b2dp_watch loops (guarded by mu): a latched Xid beats them all at once
 };
@@ -163,7 +164,9 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         std::map<std::string, std::string> kv;
         if (!parse_kv(u.substr(5), kv)) return fail(B2DP_E_INVAL, "bad cuda: uri");
         CudaConfig cfg;
+        std::string cdi_kind;
         for (auto& p : kv) {
+            if (p.first == "cdi") { cdi_kind = p.second; continue; }
             if (p.first == "devices") {
                 size_t pos = 0;
                 while (pos <= p.second.size()) {
@@ -206,6 +209,7 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         c->kind = b2dp_ctx::CUDA;
         c->sysroot = cfg.sysroot;
         c->cuda = be;
+        c->cdi_kind = cdi_kind;
         // xid=1: a device-level Xid is pushed to the kubelet at once -- every running ListAndWatch loop of this
         // context runs a heartbeat cycle now instead of at the next pulse (the reference only learns at a pulse)
         cuda_set_health_event_callback(be, [c] {
@@ -649,6 +653,21 @@ extern "C" int b2dp_allocate_response(b2dp_ctx* c, const char* const* ids, int n
         pb::bytes_field(wire, 1, entry);
     }
     for (auto& s : specs) pb::encode_devspec(wire, 3, s.container_path, s.host_path, s.permissions);
+    if (c->kind == b2dp_ctx::CUDA && !c->cdi_kind.empty()) {
+        // cdi=<kind>: ContainerAllocateResponse.cdi_devices (field 5, CDIDevice{name=1}) = "<kind>=<minor>", the
+        // fully qualified names of an nvidia-ctk generated CDI spec; a CDI-enabled runtime injects from those
+        std::vector<Device> devs;
+        rc = enumerate_ctx(c, devs);
+        if (rc != B2DP_OK) return rc;
+        for (int i = 0; i < n_ids; ++i)
+            for (const auto& d : devs)
+                if (ids[i] && d.id == ids[i]) {
+                    std::string cdi;
+                    pb::string_field(cdi, 1, c->cdi_kind + "=" + std::to_string(d.card));
+                    pb::bytes_field(wire, 5, cdi);
+                    break;
+                }
+    }
     *len = wire.size();
     if (wire.size() > cap) return B2DP_E_NOSPC;
     if (!wire.empty() && !buf) return B2DP_E_INVAL;

@@ -173,6 +173,12 @@ def test_cuda_backend_equals_reference_algorithm_on_exported_tree(P, tmp_path):
         resp = P.v1beta1.ContainerAllocateResponse.FromString(ctx.allocate_response([ids[0], "unknown"]))
         assert dict(resp.envs) == {"NVIDIA_VISIBLE_DEVICES": str(devs[ids[0]]["card"])}
         assert [d.host_path for d in resp.devices][-1] == "/dev/nvidia%d" % devs[ids[0]]["card"]
+        with P.Context("cuda:devices=0,bytes=%d,cdi=nvidia.com/gpu" % MiB) as cctx:          # optional CDI names
+            (cid,) = sorted(cctx.enumerate())
+            cresp = P.v1beta1.ContainerAllocateResponse.FromString(cctx.allocate_response([cid, "unknown"]))
+            assert [x.name for x in cresp.cdi_devices] == ["nvidia.com/gpu=%d" % cctx.enumerate()[cid]["card"]]
+            assert cresp.SerializeToString() == cctx.allocate_response([cid, "unknown"])      # canonical field order
+        assert not resp.cdi_devices
         specs = ctx.device_specs(ids)
         assert [s[0] for s in specs[:3]] == ["/dev/nvidiactl", "/dev/nvidia-uvm", "/dev/nvidia-uvm-tools"]
         assert len(specs) == 3 + len(ids)
