@@ -17,11 +17,18 @@ e2e     : K x b2dp_list_and_watch(HEARTBEAT): enumerate -> node health -> probe 
           receives the 48-byte result block per device through pinned mapped memory plus the response.
 roofline: achieved = 2*S / mean CUDA-event time of the probe kernel over the timed steps; peak =
           MEASURED_PEAKS.json hbm_gbs (else the 6650 GB/s fallback of B200_PROFILING.md).
+single_process / p2p / parity (rank 0, after the per-rank legs, every other rank idle): the DEPLOYMENT shape --
+          ONE plugin process driving all N GPUs (BASELINE.json configs[2], "<10 ms over 8 B200s"): ListAndWatch
+          heartbeat cycle p50/p99/max with one N-device response; the NVLink P2P matrix (configs[3]); and, untimed,
+          the product's answers against the oracle on the tree the product exports (device table, pair weights from
+          the MEASURED links, every allocation size, ListAndWatch list, labels).  A false parity entry fails the run.
 """
 import argparse
 import importlib
+import importlib.util
 import json
 import os
+import statistics
 import subprocess
 import sys
 import tempfile
@@ -60,6 +67,23 @@ while True:
 REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
            0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
            0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+
+def bench_config(n):
+    """The workload description, IDENTICAL in both arms (the driver compares the two `config` objects)."""
+    return {"workload": WORKLOAD, "n_devices": n, "probe_bytes_per_buffer": S_BYTES,
+            "algorithmic_bytes_per_gpu_step": 2 * S_BYTES,
+            "l2": "inputs (1 GiB per buffer) larger than the 126 MB L2; buffers ping-pong every step",
+            "parallelism": "1 unit per GPU, no data-path collective"}
+
+
+def pctl(v, q):
+    v = sorted(v)
+    return v[int(q * (len(v) - 1) + 0.5)] if v else None
+
+
+def dist3(v, nd=4):
+    return {"p50": round(pctl(v, 0.5), nd), "p99": round(pctl(v, 0.99), nd), "max": round(max(v), nd), "n": len(v)}
 
 
 class ClockSampler:
@@ -112,13 +136,25 @@ def peak_hbm():
 
 
 def traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one probe launch, from the committed ncu capture (a constant
+    read from profiles/traffic.json -- ncu cannot run inside a timed bench)."""
     try:
-        return json.load(open(os.path.join(REPO, "profiles", "traffic.json")))["hbm_probe_tma_bytes_per_launch"]
+        d = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+        return d["hbm_probe_tma_bytes_per_launch"], d.get("source", "profiles/traffic.json")
     except Exception:
-        return None
+        return None, None
 
 
-def cpu_probe_baseline(threads, budget_s=6.0, sample_bytes=256 << 20):
+def load_synth():
+    """The synthetic kfd-tree writer, loaded by FILE PATH: it is pure Python, and importing the product package
+    (which maps libb200dp.so) has no place in the CPU legs."""
+    spec = importlib.util.spec_from_file_location("b2dp_synth", os.path.join(REPO, PKG, "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_probe_baseline(threads, budget_s=6.0, sample_bytes=S_BYTES):
     """The oracle's C restatement of the probe pass streamed through host DRAM (bounded sample)."""
     import numpy as np
     from oracle import cbind
@@ -148,10 +184,9 @@ def kfd_walk_baseline(n_devices, reps=200):
     from oracle import cbind
     cbind.build()
     k = cbind.kfd_lib()
-    pkg = importlib.import_module(PKG)
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
     root = tempfile.mkdtemp(prefix="b2dp_bench_kfd_", dir=base)
-    pkg.synth.write_b200_tree(root, n_gpus=n_devices)
+    load_synth().write_b200_tree(root, n_gpus=n_devices)
     r = root.encode()
     for _ in range(3):
         k.kfdwalk_cycle(r, 1)
@@ -171,7 +206,8 @@ def kfd_walk_baseline(n_devices, reps=200):
 def run_reference(args, rank, world):
     """The reference's CPU path on the box's host cores: per step, the reference-shaped
     ListAndWatch cycle (kfd walk: enumerate x2 + text health check, C port of the Go code) followed
-    by the CPU restatement of the probe over a bounded sample per device."""
+    by the CPU restatement of the probe over the same S = 1 GiB buffer per device.  Touches nothing of the product:
+    no package import, no libb200dp.so."""
     if rank != 0:
         return
     import numpy as np
@@ -179,37 +215,35 @@ def run_reference(args, rank, world):
     from oracle import cbind
     cbind.build()
     lib, k = cbind.probe_lib(), cbind.kfd_lib()
-    pkg = importlib.import_module(PKG)
     threads = os.cpu_count() or 1
     n = args.gpus
+    warmup = max(3, args.warmup)
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
     root = tempfile.mkdtemp(prefix="b2dp_ref_kfd_", dir=base)
-    pkg.synth.write_b200_tree(root, n_gpus=n)
+    load_synth().write_b200_tree(root, n_gpus=n)
     r = root.encode()
-    # bounded sample: keep K steps within ~60 s
-    sample = 256 << 20
+    sample = S_BYTES                                  # the product arm's S: 1 GiB read + 1 GiB written per device per step
     n_words = sample // 4
     src = np.empty(n_words, dtype=np.uint32)
     dst = np.empty(n_words, dtype=np.uint32)
     seed = 0x5EED0000
     lib.oracle_fill(src.ctypes.data, n_words, seed, threads)
     out = (C.c_uint64 * 3)()
+    lib.oracle_probe_pass(src.ctypes.data, dst.ctypes.data, n_words, seed, 0, threads, out)      # page-in
     t0 = time.perf_counter()
     lib.oracle_probe_pass(src.ctypes.data, dst.ctypes.data, n_words, seed, 0, threads, out)
-    lib.oracle_probe_pass(src.ctypes.data, dst.ctypes.data, n_words, seed, 0, threads, out)
-    per_pass = (time.perf_counter() - t0) / 2
-    while sample > (16 << 20) and per_pass * n * (args.steps + args.warmup) > 60.0:
+    per_pass = time.perf_counter() - t0
+    # bounded: the whole run stays within ~2 minutes; only a slow host ever shrinks the sample, and says so
+    while sample > (16 << 20) and per_pass * n * (args.steps + warmup) > 120.0:
         sample //= 2
         per_pass /= 2
     n_words = sample // 4
 
-    def step():
+    for _ in range(warmup):
         k.kfdwalk_cycle(r, 1)
         for _ in range(n):
             lib.oracle_probe_pass(src.ctypes.data, dst.ctypes.data, n_words, seed, 0, threads, out)
-    for _ in range(max(3, args.warmup)):
-        step()
-    walk = 0.0
+    walk, step_ms = 0.0, []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         w0 = time.perf_counter()
@@ -217,22 +251,179 @@ def run_reference(args, rank, world):
         walk += time.perf_counter() - w0
         for _ in range(n):
             lib.oracle_probe_pass(src.ctypes.data, dst.ctypes.data, n_words, seed, 0, threads, out)
+        step_ms.append((time.perf_counter() - w0) * 1e3)
     dt = time.perf_counter() - t0
+    assert out[1] == 0
     import shutil
     shutil.rmtree(root, ignore_errors=True)
     value = n * 2.0 * sample * args.steps / dt / 1e9
-    sample_desc = "%d MiB of the 1 GiB per-device probe buffer per device per step, %d device(s), host DRAM" % (sample >> 20, n)
+    sample_desc = ("%d MiB of the %d MiB per-device probe buffer per device per step (%s), %d device(s), host DRAM, %d threads"
+                   % (sample >> 20, S_BYTES >> 20, "the full buffer" if sample == S_BYTES else "shrunk to bound the run", n, threads))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": n,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(dt / args.steps * 1e3, 4),
+        "steps": args.steps, "warmup": warmup, "ms_per_step": round(dt / args.steps * 1e3, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_devices": n, "note": "CPU arm: C port of the reference's kfd walk (no Go "
-                   "toolchain here) + CPU restatement of the probe on a bounded sample"},
-        "cycle_ms_kfd_walk": round(walk / args.steps * 1e3, 4),
-        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc},
+        "config": bench_config(n),
+        "arm": "CPU: C port of the reference's kfd walk (no Go toolchain here; the reference has no GPU probe) + CPU "
+               "restatement of the probe pass, all host threads",
+        "step_ms": dist3(step_ms),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc,
+                         "cycle_ms_kfd_walk": round(walk / args.steps * 1e3, 4)},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---- rank-0-only legs of the product arm ---------------------------------------------------------------------------
+def single_process_leg(pkg, n, steps, warmup, variant):
+    """ONE context over all N GPUs (the daemon's shape): the kubelet-facing heartbeat cycle, per-GPU roofline
+    fractions, and the NVLink P2P matrix.  Returns (ctx, single_process dict, p2p dict)."""
+    N = pkg._native
+    peak, _ = peak_hbm()
+    uri = "cuda:bytes=%d,devices=%s" % (S_BYTES, "+".join(str(i) for i in range(n)))
+    t0 = time.perf_counter()
+    ctx = pkg.Context(uri)
+    open_s = time.perf_counter() - t0
+    ctx.list_and_watch("gpu", N.LW_INITIAL)
+    t_w, i = time.perf_counter(), 0
+    while i < warmup or time.perf_counter() - t_w < 0.1:
+        ctx.list_and_watch("gpu", N.LW_HEARTBEAT, variant=variant)
+        i += 1
+    cyc, kmax, host, unhealthy = [], [], [], 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        wire, st = ctx.list_and_watch("gpu", N.LW_HEARTBEAT, variant=variant)
+        dt = (time.perf_counter() - t0) * 1e3
+        cyc.append(dt)
+        kmax.append(st.probe_ms_device_max)
+        host.append(dt - st.probe_ms_device_max)
+        unhealthy += st.n_unhealthy
+    msg = pkg.v1beta1.ListAndWatchResponse.FromString(wire)
+    assert len(msg.devices) == n and all(d.health == "Healthy" for d in msg.devices), msg
+    per_gpu = [[] for _ in range(n)]
+    refs = [0.0] * n
+    for _ in range(max(20, steps // 10)):
+        for r in ctx.probe_health(variant=variant):              # CUDA-event timed, like the roofline leg
+            per_gpu[r.device].append(r.gbs)
+            refs[r.device] = r.gbs_ref
+    p50 = pctl(cyc, 0.5)
+    sp = {"n_devices": n, "uri": uri, "open_s": round(open_s, 3), "cycles": steps,
+          "cycle_ms_p50": round(p50, 4), "cycle_ms_p99": round(pctl(cyc, 0.99), 4), "cycle_ms_max": round(max(cyc), 4),
+          "response_bytes": len(wire), "unhealthy_verdicts": unhealthy,
+          "per_gpu_gbs": [round(statistics.median(g), 1) for g in per_gpu],
+          "per_gpu_frac": [round(statistics.median(g) / peak, 4) for g in per_gpu],
+          "per_gpu_calibrated_ceiling_gbs": [round(x, 1) for x in refs],
+          "aggregate_gbs": round(n * 2.0 * S_BYTES / (p50 * 1e-3) / 1e9, 1),
+          # tail attribution: the slowest GPU's in-kernel span (first CTA start .. result published) of each cycle vs
+          # everything the host adds around it (enqueue on N streams, polling, merge, protobuf, the Python call)
+          "slowest_kernel_ms": dist3(kmax), "host_overhead_ms": dist3(host),
+          "target_ms": 10.0, "under_target": bool(pctl(cyc, 0.99) < 10.0)}
+    p2p = {"pairs": 0}
+    if n > 1:
+        t0 = time.perf_counter()
+        gbs, lt, mm = ctx.p2p_matrix()
+        off = sorted(float(gbs[i, j]) for i in range(n) for j in range(n) if i != j)
+        classes = {}
+        for i in range(n):
+            for j in range(n):
+                if i != j:
+                    classes[str(int(lt[i, j]))] = classes.get(str(int(lt[i, j])), 0) + 1
+        p2p = {"pairs": len(off), "bytes_per_pair": 256 << 20, "matrix_s": round(time.perf_counter() - t0, 3),
+               "gbs_min": round(off[0], 1), "gbs_median": round(statistics.median(off), 1), "gbs_max": round(off[-1], 1),
+               "frac_of_770": round(statistics.median(off) / 770.0, 4), "mismatches": int(mm.sum()),
+               "link_classes": classes,
+               "note": "one direction of every pair per half-round, N-1 rounds of disjoint matchings; 770 GB/s = measured "
+                       "peer-copy reference (B200_PROFILING.md)"}
+    return ctx, sp, p2p
+
+
+def parity_block(pkg, ctx, n):
+    """UNTIMED checker leg (after every timed region): the product's answers on the live node against the oracle
+    (the CPU restatement of the reference) on the kfd-shaped tree the product exports -- BASELINE.json's
+    "bit-exact on integer fields ... when both are pointed at equivalent fixtures"."""
+    import shutil
+    from oracle import allocator as oalloc
+    from oracle import amdgpu as oamd
+    from oracle import labeller as olab
+    from oracle import plugin as oplug
+    from oracle import probe as oprobe
+    N = pkg._native
+    root = tempfile.mkdtemp(prefix="b2dp_parity_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    out = {}
+    try:
+        devs = ctx.enumerate()
+        ctx.export_kfd_tree(root)                       # measures the P2P links if they have not been yet
+        want = oamd.GetAMDGPUs(root)
+        out["enumerate"] = devs == want and len(devs) == n
+        ids = sorted(devs)
+        rc = ctx.start()
+        opol = oalloc.BestEffortPolicy()
+        oerr = opol.Init(oplug.getDevices(root), root + "/sys/class/kfd/kfd/topology/nodes")
+        if n > 1:
+            out["pair_weights"] = rc == 0 and oerr is None and ctx.pair_weights() == opol.p2pWeights
+            ok = rc == 0 and oerr is None
+            for size in range(1, n + 1):
+                ok = ok and ctx.preferred_allocation(ids, [], size) == opol.Allocate(list(ids), [], size)[0]
+            for must in (ids[-1:], ids[:1] + ids[-1:]):
+                for size in range(len(must), n + 1):
+                    ok = ok and ctx.preferred_allocation(ids, must, size) == opol.Allocate(list(ids), list(must), size)[0]
+            out["allocations_all_sizes"] = ok
+        else:                                           # one device: both sides must refuse the same way
+            out["pair_weights"] = rc == N.E_ALLOC_NO_WEIGHTS and oerr is not None
+            out["allocations_all_sizes"] = not ctx.preferred_allocation_available()
+        wire, _ = ctx.list_and_watch("gpu", N.LW_INITIAL)
+        homog, lw = oplug.list_and_watch_devices(want, "gpu")
+        msg = pkg.v1beta1.ListAndWatchResponse.FromString(wire)
+        out["list_and_watch"] = ([(d.ID, d.health, d.topology.nodes[0].ID) for d in msg.devices] == lw
+                                 and msg.SerializeToString() == wire
+                                 and ctx.resource_list("single") == oplug.getResourceList("single", root)[0])
+        out["node_health"] = ctx.node_health() == oplug.simpleHealthCheck(root + "/sys/class/kfd/kfd")
+        gens = ["driver-version", "driver-src-version", "device-id", "product-name", "vram", "simd-count", "cu-count",
+                "compute-memory-partition", "compute-partitioning-supported", "memory-partitioning-supported",
+                "family", "firmware"]
+        drm = {}
+        for v in want.values():
+            b = "%s/sys/class/drm/card%d/device/" % (root, v["card"])
+            fw = dict(ln.split(" ", 1) for ln in open(b + "b2dp_firmware").read().splitlines()) if os.path.exists(b + "b2dp_firmware") else {}
+            fw = {k: "".join(ch if ch.isalnum() or ch in ".-_" else "_" for ch in ver.strip()) for k, ver in fw.items()}
+            fam = open(b + "b2dp_family").read().strip() if os.path.exists(b + "b2dp_family") else ""
+            drm["card%d" % v["card"]] = {"family": fam, "feat": {}, "fw": fw}
+        got = ctx.generate_labels(gens)
+        out["labels"] = got == olab.generateLabels({g: True for g in gens}, root, drm=drm) and len(got) >= 10
+        # the probe's integer results against the oracle's closed form, every device, 1 GiB
+        ok = True
+        for r in ctx.probe_health():
+            ok = ok and r.mismatches == 0 and r.checksum == r.expected_checksum == oprobe.expected_checksum(S_BYTES // 4, r.seed)
+        out["probe_checksums"] = ok
+        out["label_count"] = len(got)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return out
+
+
+class FileFlag:
+    """Rank 0 works alone while the other ranks sleep on a file (an NCCL barrier would park a spinning kernel on
+    every GPU that rank 0 is about to measure)."""
+
+    def __init__(self):
+        key = "%s_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "none"), os.getppid())
+        self.path = os.path.join(tempfile.gettempdir(), "b2dp_bench_flag_" + key)
+
+    def clear(self):
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+    def set(self):
+        open(self.path, "w").close()
+
+    def wait(self, timeout=900.0):
+        t0 = time.time()
+        while not os.path.exists(self.path):
+            if time.time() - t0 > timeout:
+                raise SystemExit("rank 0 never finished its single-process leg")
+            time.sleep(0.02)
 
 
 def main():
@@ -242,6 +433,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--variant", type=int, default=0, help="0 = TMA-staged kernel (default), 1 = register path")
+    ap.add_argument("--single-cycles", type=int, default=0, help="cycles of the single-process leg (default max(steps, 500))")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries (NCCL prints its version banner there) are
     # diverted to stderr for the whole run and the line is written to the saved descriptor.
@@ -264,6 +456,9 @@ def main():
     pkg = importlib.import_module(PKG)      # raises if libb200dp.so is missing
     N = pkg._native
     ranks = importlib.import_module(PKG + ".ranks")
+    flag = FileFlag()
+    if rank == 0:
+        flag.clear()
     rg = ranks.RankGroup(backend="nccl")   # barrier + timing reductions only; no data-path collective
     ctx = pkg.Context("cuda:devices=%d,bytes=%d" % (local_rank, S_BYTES))
     barrier, max_over_ranks, sum_over_ranks = rg.barrier, rg.max, rg.sum
@@ -284,16 +479,20 @@ def main():
     # ---- value leg: the probe through the C ABI, buffers resident ------------------------------
     warm(lambda: ctx.probe_health(variant=args.variant))
     barrier()
-    kernel_ms, unhealthy = [], 0
+    kernel_ms, unhealthy, value_ms, fracs = [], 0, [], []
     w0 = time.monotonic_ns()
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        s0 = time.perf_counter()
         res = ctx.probe_health(variant=args.variant)
+        value_ms.append((time.perf_counter() - s0) * 1e3)
         kernel_ms.append(res[0].ms_event)
+        fracs.append(res[0].frac)
         unhealthy += sum(0 if r.healthy else 1 for r in res)
     torch.cuda.synchronize()
     t_value = time.perf_counter() - t0
     windows.append((w0, time.monotonic_ns()))
+    gbs_ref = res[0].gbs_ref
     barrier()
     t_value = max_over_ranks(t_value)
 
@@ -327,10 +526,13 @@ def main():
     warm(lambda: ctx.list_and_watch("gpu", N.LW_HEARTBEAT, variant=args.variant))
     barrier()
     enum_ms = enc_ms = 0.0
+    e2e_ms = []
     w0 = time.monotonic_ns()
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        s0 = time.perf_counter()
         wire, st = ctx.list_and_watch("gpu", N.LW_HEARTBEAT, variant=args.variant)
+        e2e_ms.append((time.perf_counter() - s0) * 1e3)
         unhealthy += st.n_unhealthy
         enum_ms += st.ms_enumerate
         enc_ms += st.ms_encode
@@ -342,6 +544,7 @@ def main():
     unhealthy = sum_over_ranks(float(unhealthy))
     kernel_ms_mean = sum(kernel_ms) / len(kernel_ms)
     kernel_ms_max_rank = max_over_ranks(kernel_ms_mean)
+    e2e_p99_max_rank = max_over_ranks(pctl(e2e_ms, 0.99))
     msg = pkg.v1beta1.ListAndWatchResponse.FromString(wire)
     assert len(msg.devices) == 1 and msg.devices[0].health == "Healthy", msg
 
@@ -361,7 +564,6 @@ def main():
     grpc_ms = None
     try:
         import grpc
-        import statistics
         srv_mod = importlib.import_module(PKG + ".server")
         V = pkg.v1beta1
         d = tempfile.mkdtemp(prefix="b2b_", dir="/tmp")
@@ -386,22 +588,43 @@ def main():
         print("grpc leg skipped: %r" % (e,), file=sys.stderr)
         grpc_ms = max_over_ranks(-1.0)
 
-    # ---- the same, with the native daemon (b200dp_plugind: C++ gRPC host, own process, own probe ring on this
-    # GPU): SIGUSR1 "heartbeat now" -> probe -> ListAndWatchResponse received by a grpcio client; rank 0 only --
-    native_ms = None
+    # ---- the per-rank legs are over: every rank gives its GPU back, then rank 0 alone drives all N GPUs from ONE
+    # process (the deployment shape) while the others sleep on a file ----------------------------------------------
+    ctx.close()
+    barrier()
+    sp = p2p = parity = native_ms = None
+    failed = None
     if rank == 0:
         try:
-            dp = importlib.import_module(PKG + ".daemon_probe")
-            native_ms = dp.heartbeat_latency_ms("cuda:devices=%d,bytes=%d" % (local_rank, S_BYTES), iters=100)
-        except Exception as e:      # noqa: BLE001
-            print("native daemon leg skipped: %r" % (e,), file=sys.stderr)
+            w0 = time.monotonic_ns()
+            cycles = args.single_cycles or max(args.steps, 500)
+            sctx, sp, p2p = single_process_leg(pkg, world, cycles, warmup, args.variant)
+            windows.append((w0, time.monotonic_ns()))
+            try:
+                parity = parity_block(pkg, sctx, world)
+            finally:
+                sctx.close()
+            # the same with the native daemon (b200dp_plugind: C++ gRPC host, own process, its own context over all N
+            # GPUs): SIGUSR1 "heartbeat now" -> probe fan-out -> ListAndWatchResponse received by a grpcio client
+            try:
+                dp = importlib.import_module(PKG + ".daemon_probe")
+                native_ms = dp.heartbeat_latency_ms(sp["uri"], iters=100)
+            except Exception as e:      # noqa: BLE001
+                print("native daemon leg skipped: %r" % (e,), file=sys.stderr)
+        except BaseException as e:      # noqa: BLE001  (the other ranks must be released whatever happens here)
+            failed = e
+        flag.set()
+    else:
+        flag.wait()
     barrier()
 
     clocks = sampler.stop(windows) if sampler else None
     if rank != 0:
-        ctx.close()
         rg.close()
         return
+    if failed is not None:
+        rg.close()
+        raise failed
 
     bytes_per_step_per_gpu = 2.0 * S_BYTES
     n = world
@@ -409,29 +632,44 @@ def main():
     e2e_value = n * bytes_per_step_per_gpu * args.steps / t_e2e / 1e9
     peak, peak_src = peak_hbm()
     achieved = bytes_per_step_per_gpu / (kernel_ms_mean * 1e-3) / 1e9
+    traffic, traffic_src = traffic_per_launch()
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": warmup,
         "ms_per_step": round(t_value / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "probe_bytes_per_buffer": S_BYTES, "algorithmic_bytes_per_gpu_step": int(bytes_per_step_per_gpu),
-                   "kernel": "hbm_probe_tma<4,1024,3> grid=2xSMs" if args.variant == 0 else "hbm_probe_r128<512,2> grid=2xSMs",
-                   "l2": "inputs (1 GiB per buffer) larger than the 126 MB L2; buffers ping-pong every step",
-                   "parallelism": "1 process per GPU, no data-path collective"},
+        "config": bench_config(n),
+        "arm": "B200: " + ("hbm_probe_tma<4,1024,3> grid=2xSMs" if args.variant == 0 else "hbm_probe_r128<512,2> grid=2xSMs")
+               + ", 1 process per GPU for value/e2e (the driver's launch shape), ONE process over all GPUs for single_process/p2p",
+        "step_ms": dist3(value_ms),
         "cycle_ms": round(t_e2e / args.steps * 1e3, 4),
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 48 * 1 + len(wire),
-                "cycle_ms": round(t_e2e / args.steps * 1e3, 4), "ms_enumerate": round(enum_ms / args.steps, 5),
+                "cycle_ms": round(t_e2e / args.steps * 1e3, 4), "cycle_ms_dist": dist3(e2e_ms),
+                "cycle_ms_p99_slowest_rank": round(e2e_p99_max_rank, 4),
+                "ms_enumerate": round(enum_ms / args.steps, 5),
                 "ms_encode": round(enc_ms / args.steps, 5), "response_bytes": len(wire),
                 "stream_start_ms": round(stream_start_ms, 4),
                 "heartbeat_to_kubelet_grpc_ms": None if grpc_ms is None or grpc_ms < 0 else round(grpc_ms, 4),
                 "heartbeat_to_kubelet_native_daemon_ms": native_ms,
-                "note": "no bulk host buffers on this path: kernel arguments in, 48-byte result block (pinned mapped) + serialized response out; the value leg brackets every kernel with CUDA events (the roofline's clock), the kubelet-facing call completes on the published result block alone"},
+                "note": "no bulk host buffers exist on this path, so there is nothing to copy host->device: per step the host "
+                        "passes kernel arguments and reads back the 48-byte result block the last CTA publishes into pinned "
+                        "mapped memory plus the serialized response -- those %d bytes ARE the entire per-step result (the "
+                        "device->host 'copy' is the GPU's own store, not a cudaMemcpy). The value leg brackets every kernel "
+                        "with CUDA events (the roofline's clock); the kubelet-facing call completes on the published result "
+                        "block alone. heartbeat_to_kubelet_native_daemon_ms is one daemon over all %d GPU(s)."
+                        % (48 + len(wire), n)},
         "gpu_launches": args.steps * n,
         "unhealthy_verdicts": int(unhealthy),
+        "health_floor": {"min_frac": 0.8, "calibrated_ceiling_gbs": round(gbs_ref, 1),
+                         "frac_of_ceiling": dist3(fracs), "floor_gbs": round(0.8 * gbs_ref, 1),
+                         "note": "Healthy needs >= 0.8 x the ceiling calibrated when the context opened (best warm pass, max over "
+                                 "sibling GPUs); expected_checksum is the host's closed form"},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": traffic_per_launch(), "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel_ms_mean": round(kernel_ms_mean, 5), "kernel_ms_mean_slowest_rank": round(kernel_ms_max_rank, 5),
+                     "kernel_ms_dist": dist3(kernel_ms, 5),
                      "driver_d2d_copy_gbs_same_run": None if drv_copy_gbs is None else round(drv_copy_gbs, 1),
                      "note": "driver_d2d_copy = torch copy_ of the same 1 GiB (best of 20, CUDA events): the mixed read+write ceiling of this part; the probe verifies and re-keys every word at that rate"},
+        "single_process": sp, "p2p": p2p, "parity": parity,
         "clocks": clocks,
     }
     # the reference's own sysfs/kfd CPU path on this box's host cores, in the same run, at every N
@@ -440,15 +678,16 @@ def main():
     start_ms, beat_ms = kfd_walk_baseline(n)
     line["reference_cpu_path"] = {"kfd_walk_stream_start_ms": round(start_ms, 4), "kfd_walk_heartbeat_ms": round(beat_ms, 4),
                                   "n_devices": n, "threads": 1, "host_cores": os.cpu_count(), "kind": "port"}
-    if n == 1:
-        threads = os.cpu_count() or 1
-        cpu_gbs, passes, dt = cpu_probe_baseline(threads)
-        line["cpu_baseline"] = {"value": round(cpu_gbs, 2), "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "256 MiB of the 1 GiB probe buffer, %d passes in %.1f s, host DRAM" % (passes, dt),
-                                "kfd_walk_stream_start_ms": round(start_ms, 4), "kfd_walk_heartbeat_ms": round(beat_ms, 4)}
+    threads = os.cpu_count() or 1
+    cpu_gbs, passes, dt = cpu_probe_baseline(threads, budget_s=6.0 if n == 1 else 3.0)
+    line["cpu_baseline"] = {"value": round(cpu_gbs, 2), "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": "the 1 GiB probe buffer of ONE device, %d passes in %.1f s, host DRAM, %d threads" % (passes, dt, threads),
+                            "cycle_ms_kfd_walk": round(start_ms, 4), "kfd_walk_heartbeat_ms": round(beat_ms, 4)}
     print(json.dumps(line), flush=True)
-    ctx.close()
     rg.close()
+    bad = [k for k, v in (parity or {}).items() if v is False]
+    if bad:
+        raise SystemExit("parity FAILED against the oracle: %s" % ", ".join(bad))
 
 
 if __name__ == "__main__":

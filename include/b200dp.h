@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define B2DP_ABI_VERSION 2
+#define B2DP_ABI_VERSION 3
 #if defined(__GNUC__)
 #define B2DP_API __attribute__((visibility("default")))
 #else
@@ -132,7 +132,15 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     default 1073741824>, slots=<buffers in the probe ring, default 2 = ping-pong; with M
  *                     slots pass k verifies slot k mod M (written by pass k-1) and re-keys it into slot
  *                     k+1 mod M, so M heartbeats scrub M*S bytes of HBM>,
- *                     min_gbs=<health threshold, default 3000>,
+ *                     min_frac=<Healthy needs achieved GB/s >= min_frac x the device's ceiling, default 0.8 (BASELINE.json:
+ *                     "each per-GPU probe >= 80 % of HBM peak"); the ceiling (gbs_ref) is calibrated when the context
+ *                     opens: calib=<K, default 3> warm non-advancing passes per GPU, best kept, then the maximum over the
+ *                     GPUs of the same product and ring size, so a part that is already slow at start-up is judged
+ *                     against its siblings>, ref_gbs=<pin the ceiling instead of calibrating, e.g. the site's measured
+ *                     peak>, min_gbs=<absolute GB/s floor, overrides min_frac; default none>.  The fractional floor
+ *                     applies to rings that stream from HBM (slot >= 128 MiB, above the 126 MB L2); a pass below the floor
+ *                     on a GPU that another process is using at that moment (NVML) is flagged B2DP_RES_CONTENDED and judged
+ *                     on integrity alone,
  *                     sysroot=<dir for numa_node lookups, default "/">, p2p_bytes=<default 268435456>,
  *                     busy=probe|skip|shrink (what to do on a GPU another process is using; default probe),
  *                     shrink_bytes=<prefix verified by busy=shrink, default 67108864>, ecc=1 (also fail on new
@@ -141,7 +149,12 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     43, 45, 68, 109 are ignored; a listener thread waits on the NVML event set and, when a
  *                     device-level Xid arrives, every running b2dp_watch loop of the context sends a heartbeat
  *                     cycle at once instead of at its next pulse).
- *                     cdi=<kind> (e.g. cdi=nvidia.com/gpu): Allocate also returns cdi_devices "<kind>=<minor>".
+ *                     cdi=<kind> (e.g. cdi=nvidia.com/gpu): Allocate also returns cdi_devices "<kind>=<GPU UUID>";
+ *                     id_strategy=uuid|index (default uuid): what NVIDIA_VISIBLE_DEVICES and the CDI names carry -- the
+ *                     GPU/MIG UUID or the NVML index (never the /dev/nvidia minor, which the runtime would misread).
+ *                     mig=auto|off (default auto): with MIG mode enabled on a GPU (NVML), its MIG devices are enumerated
+ *                     instead of the GPU (ids "nvidia_mig_<gpu>_<gi>_<ci>", dev_id of the parent, partition strings
+ *                     "<N>g"/"<M>gb") and probed by one helper process per instance.
  *                     A GPU whose own setup fails (or that break=<i>+<j>, a test hook, names by enumeration index)
  *                     stays in the device list and is reported Unhealthy with B2DP_E_CUDA on every pass; the open
  *                     only fails when no GPU could be set up.
@@ -174,8 +187,9 @@ B2DP_API int b2dp_node_health(b2dp_ctx *ctx, int32_t *healthy);
 typedef struct b2dp_probe_opts {
     uint32_t timeout_ms;   /* per-call deadline; 0 = 5000 (the exporter RPC timeout, health.go:37) */
     uint32_t flags;        /* B2DP_PROBE_* */
-    float min_gbs;         /* Healthy needs achieved GB/s >= this; 0 = context default */
-    uint32_t reserved;
+    float min_gbs;         /* absolute floor: Healthy needs achieved GB/s >= this; 0 = context default (min_frac x gbs_ref) */
+    uint32_t grid_ctas;    /* diagnostic hook: launch the pass on this many CTAs instead of the tuned 2 x SMs (emulates a
+                              part that lost bandwidth: the data is verified all the same, only slower); 0 = default */
 } b2dp_probe_opts;
 #define B2DP_PROBE_VARIANT_TMA 0u        /* smem-staged bulk-copy kernel (default) */
 #define B2DP_PROBE_VARIANT_R128 1u       /* register-path kernel (for A/B measurement) */
@@ -202,6 +216,10 @@ typedef struct b2dp_probe_result {
     float ms_device;            /* %globaltimer span inside the kernel: first CTA start .. result published */
     float gbs;                  /* bytes / ms_event when event-timed, else bytes / ms_device */
     uint32_t flags;             /* B2DP_RES_* */
+    float gbs_ref;              /* this device's ceiling: calibrated at open / ref_gbs= / b2dp_probe_set_ref */
+    float frac;                 /* gbs / gbs_ref (0 if there is no ceiling) */
+    float min_gbs_applied;      /* the floor the verdict used: min_gbs, else min_frac x gbs_ref, else 0 (none) */
+    uint32_t reserved;
 } b2dp_probe_result;
 #define B2DP_RES_SKIPPED_BUSY 0x1u /* busy=skip: another process owns the GPU, no pass ran, the last verdict stands */
 #define B2DP_RES_SHRUNK 0x2u       /* busy=shrink: a prefix (shrink_bytes) was verified without re-keying; no GB/s floor */
@@ -209,6 +227,11 @@ typedef struct b2dp_probe_result {
                                       remapping (nvmlDeviceGetRemappedRows) => Unhealthy */
 #define B2DP_RES_SMALL_RING 0x10u  /* HBM was short when the context opened (e.g. a restart under running pods): the ring
                                       slots on this GPU are smaller than bytes=; `bytes` reports what a pass moved; no GB/s floor */
+#define B2DP_RES_CONTENDED 0x20u   /* the pass ran below its GB/s floor while another process was using the GPU (NVML): not a
+                                      verdict on the part -- integrity decides alone */
+#define B2DP_RES_NO_FLOOR 0x40u    /* no GB/s floor applied: the ring slot is below 128 MiB (a pass out of the L2 says nothing
+                                      about HBM) and no absolute min_gbs was given */
+#define B2DP_RES_SLOW 0x80u        /* achieved GB/s was below min_gbs_applied */
 #define B2DP_RES_XID 0x8u          /* xid=1: a critical Xid event was delivered for this device since open (or the
                                       last b2dp_probe_reset) => Unhealthy, sticky */
 
@@ -222,6 +245,12 @@ B2DP_API int b2dp_probe_health(b2dp_ctx *ctx, const b2dp_probe_opts *opts, b2dp_
 B2DP_API int b2dp_probe_inject_fault(b2dp_ctx *ctx, int device, uint64_t word_index, uint32_t mask);
 /* Re-fill the probe buffers of `device` (-1 = all) with a clean pattern; also clears a latched Xid. */
 B2DP_API int b2dp_probe_reset(b2dp_ctx *ctx, int device);
+/* Set the bandwidth ceiling (gbs_ref) of `device` (-1 = all) the fractional floor refers to, e.g. to the site's measured
+ * HBM peak; gbs_ref <= 0 restores the device's own calibration.  Also how tests move a device across the 0.8 line. */
+B2DP_API int b2dp_probe_set_ref(b2dp_ctx *ctx, int device, float gbs_ref);
+/* Closed-form checksum of a clean probe buffer of n_words 32-bit words keyed with `seed`, computed on the host
+ * (the value b2dp_probe_result.expected_checksum carries).  No context, no GPU. */
+B2DP_API int b2dp_expected_checksum(uint64_t n_words, uint32_t seed, uint64_t *checksum);
 /* Copy `n_words` words starting at `word_index` of the buffer the next probe will read
  * (parity tests compare it with the oracle's pattern). */
 B2DP_API int b2dp_probe_peek(b2dp_ctx *ctx, int device, uint64_t word_index, uint32_t *out, uint64_t n_words);
@@ -267,6 +296,8 @@ typedef struct b2dp_cycle_stats {
     uint64_t probe_bytes;     /* algorithmic bytes over all devices */
     float ms_link_check;      /* B2DP_LW_LINK_CHECK: time of the P2P matrix */
     int32_t n_link_faults;    /* directed pairs that failed the link check */
+    float probe_ms_device_max; /* slowest device's in-kernel span (first CTA start .. result published) this cycle */
+    float probe_frac_min;     /* min over devices of gbs / gbs_ref, 0 if no probe ran or no ceiling */
 } b2dp_cycle_stats;
 
 /* One ListAndWatch send.  Writes the serialized v1beta1.ListAndWatchResponse protobuf
@@ -301,8 +332,9 @@ B2DP_API void b2dp_watch_stop(b2dp_watch *w);
  * cuda backend: /dev/nvidiactl, /dev/nvidia-uvm, /dev/nvidia-uvm-tools, then /dev/nvidia<minor>. */
 B2DP_API int b2dp_device_specs(b2dp_ctx *ctx, const char *const *ids, int n_ids, b2dp_devspec *out, int cap, int *n);
 /* Same, serialized as v1beta1.ContainerAllocateResponse (api.proto: devices=3).  The cuda backend also sets
- * envs["NVIDIA_VISIBLE_DEVICES"] = the allocated /dev/nvidia minors ("void" if none) and, with the cdi=<kind> URI
- * option, cdi_devices (field 5) "<kind>=<minor>"; the kfd backend sets neither, like the reference. */
+ * envs["NVIDIA_VISIBLE_DEVICES"] = the allocated GPU (or MIG) UUIDs -- NVML indices with id_strategy=index; "void" if
+ * none -- and, with the cdi=<kind> URI option, cdi_devices (field 5) "<kind>=<same identifier>"; the kfd backend sets
+ * neither, like the reference. */
 B2DP_API int b2dp_allocate_response(b2dp_ctx *ctx, const char *const *ids, int n_ids, uint8_t *buf, size_t cap, size_t *len);
 
 /* ---- allocator (internal/pkg/allocator) ------------------------------------------ */
@@ -336,6 +368,9 @@ B2DP_API int b2dp_allocator_allocate(b2dp_allocator *a, const char *const *avail
  * backend's topology (kfd: sysfs link files; cuda: the measured P2P matrix, running it if
  * it has not run yet).  A failure is remembered like allocatorInitError (plugin.go:86-90). */
 B2DP_API int b2dp_start(b2dp_ctx *ctx);
+/* device.go:220-252 p2pWeights of the context's own allocator (the one b2dp_start() built; cuda: from the measured
+ * P2P matrix), same row format as b2dp_allocator_pair_weights.  B2DP_E_ALLOC_INIT before b2dp_start(). */
+B2DP_API int b2dp_pair_weights(b2dp_ctx *ctx, b2dp_pair_weight *out, int cap, int *n, int *n_rows);
 /* plugin.go:210-217 GetDevicePluginOptions: 1 unless Start() failed. */
 B2DP_API int b2dp_preferred_allocation_available(b2dp_ctx *ctx, int32_t *available);
 /* plugin.go:337-351 GetPreferredAllocation for one container request. */

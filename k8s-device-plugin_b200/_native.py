@@ -36,6 +36,7 @@ PROBE_VARIANT_TMA, PROBE_VARIANT_R128 = 0, 1
 PROBE_VIA_WORKERS = 0x10
 PROBE_EVENT_TIMING = 0x20
 RES_SKIPPED_BUSY, RES_SHRUNK, RES_ECC, RES_XID, RES_SMALL_RING = 1, 2, 4, 8, 16
+RES_CONTENDED, RES_NO_FLOOR, RES_SLOW = 0x20, 0x40, 0x80
 LW_INITIAL, LW_HEARTBEAT, LW_EXTERNAL_SOURCE, LW_NO_PROBE, LW_LINK_CHECK = 1, 2, 4, 8, 16
 
 Id64 = C.c_char * 64
@@ -72,14 +73,15 @@ class FwEntry(C.Structure):
 
 
 class ProbeOpts(C.Structure):
-    _fields_ = [("timeout_ms", C.c_uint32), ("flags", C.c_uint32), ("min_gbs", C.c_float), ("reserved", C.c_uint32)]
+    _fields_ = [("timeout_ms", C.c_uint32), ("flags", C.c_uint32), ("min_gbs", C.c_float), ("grid_ctas", C.c_uint32)]
 
 
 class ProbeResult(C.Structure):
     _fields_ = [("device", C.c_int32), ("healthy", C.c_int32), ("err", C.c_int32), ("seed", C.c_uint32),
                 ("checksum", C.c_uint64), ("expected_checksum", C.c_uint64), ("mismatches", C.c_uint64),
                 ("first_bad_word", C.c_uint64), ("bytes", C.c_uint64), ("ms_event", C.c_float),
-                ("ms_device", C.c_float), ("gbs", C.c_float), ("flags", C.c_uint32)]
+                ("ms_device", C.c_float), ("gbs", C.c_float), ("flags", C.c_uint32), ("gbs_ref", C.c_float),
+                ("frac", C.c_float), ("min_gbs_applied", C.c_float), ("reserved", C.c_uint32)]
 
 
 class CycleOpts(C.Structure):
@@ -92,7 +94,7 @@ class CycleStats(C.Structure):
                 ("node_healthy", C.c_int32), ("ms_total", C.c_float), ("ms_enumerate", C.c_float),
                 ("ms_probe", C.c_float), ("ms_encode", C.c_float), ("probe_gbs_min", C.c_float),
                 ("probe_gbs_sum", C.c_float), ("probe_bytes", C.c_uint64), ("ms_link_check", C.c_float),
-                ("n_link_faults", C.c_int32)]
+                ("n_link_faults", C.c_int32), ("probe_ms_device_max", C.c_float), ("probe_frac_min", C.c_float)]
 
 
 class P2pOpts(C.Structure):
@@ -135,6 +137,8 @@ SIGNATURES = {
     "b2dp_probe_inject_fault": (_i, [_vp, _i, C.c_uint64, C.c_uint32]),
     "b2dp_probe_reset": (_i, [_vp, _i]),
     "b2dp_probe_peek": (_i, [_vp, _i, C.c_uint64, _P(C.c_uint32), C.c_uint64]),
+    "b2dp_probe_set_ref": (_i, [_vp, _i, C.c_float]),
+    "b2dp_expected_checksum": (_i, [C.c_uint64, C.c_uint32, _P(C.c_uint64)]),
     "b2dp_merge_health": (_i, [_P(Id64), _i, C.c_int32, _i, _P(Id64), _i32p, _i, _i32p]),
     "b2dp_list_and_watch": (_i, [_vp, _cp, _P(CycleOpts), _u8p, C.c_size_t, _szp, _P(CycleStats)]),
     "b2dp_watch_start": (_i, [_vp, _cp, C.c_uint32, _P(CycleOpts), WatchCb, _vp, _P(_vp)]),
@@ -151,6 +155,7 @@ SIGNATURES = {
     "b2dp_allocator_candidates": (_i, [_vp, _strs, _i, _strs, _i, _i, _i32p, _i32p]),
     "b2dp_allocator_allocate": (_i, [_vp, _strs, _i, _strs, _i, _i, _P(Id64), _i, _ip]),
     "b2dp_start": (_i, [_vp]),
+    "b2dp_pair_weights": (_i, [_vp, _P(PairWeight), _i, _ip, _ip]),
     "b2dp_preferred_allocation_available": (_i, [_vp, _i32p]),
     "b2dp_preferred_allocation": (_i, [_vp, _strs, _i, _strs, _i, _i, _P(Id64), _i, _ip]),
     "b2dp_p2p_matrix": (_i, [_vp, _P(P2pOpts), _P(C.c_float), _i32p, _P(C.c_uint64), _i]),
@@ -161,7 +166,7 @@ SIGNATURES = {
     "b2dp_generate_labels": (_i, [_vp, _cp, _P(Label), _i, _ip]),
     "b2dp_remove_old_node_labels": (_i, [_P(Label), _i, _ip]),
 }
-ABI_VERSION = 2          # must equal B2DP_ABI_VERSION in include/b200dp.h (struct layouts above)
+ABI_VERSION = 3          # must equal B2DP_ABI_VERSION in include/b200dp.h (struct layouts above)
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)   # AttributeError here = the .so does not export what the header declares
     _fn.restype = _res

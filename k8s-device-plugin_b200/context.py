@@ -22,6 +22,9 @@ class ProbeResult:
     ms_device: float
     gbs: float
     flags: int = 0
+    gbs_ref: float = 0.0           # the device's calibrated ceiling
+    frac: float = 0.0              # gbs / gbs_ref
+    min_gbs_applied: float = 0.0   # the floor the verdict used
 
 
 @dataclass
@@ -39,6 +42,8 @@ class CycleStats:
     probe_bytes: int
     ms_link_check: float = 0.0
     n_link_faults: int = 0
+    probe_ms_device_max: float = 0.0
+    probe_frac_min: float = 0.0
 
 
 class Context:
@@ -113,23 +118,28 @@ class Context:
         return bool(v.value)
 
     def probe_health(self, timeout_ms=0, variant=N.PROBE_VARIANT_TMA, min_gbs=0.0, via_workers=False,
-                     timed=True) -> List[ProbeResult]:
+                     timed=True, grid_ctas=0) -> List[ProbeResult]:
         """One fan-out pass.  timed=True brackets each kernel with CUDA events (ms_event, what the roofline
         is measured with); timed=False is the kubelet-facing configuration (completion by the published
         result block alone, GB/s from the in-kernel timer)."""
         opts = N.ProbeOpts(timeout_ms, variant | (N.PROBE_VIA_WORKERS if via_workers else 0)
-                           | (N.PROBE_EVENT_TIMING if timed else 0), min_gbs, 0)
+                           | (N.PROBE_EVENT_TIMING if timed else 0), min_gbs, grid_ctas)
         rc, arr, n = N.grow_call(lambda cap: (N.ProbeResult * cap)(),
                                  lambda a, cap, pn: N.lib.b2dp_probe_health(self._h, C.byref(opts), a, cap, pn))
         N.check(rc, self._h)
         return [ProbeResult(r.device, bool(r.healthy), r.err, r.seed, r.checksum, r.expected_checksum, r.mismatches,
-                            r.first_bad_word, r.bytes, r.ms_event, r.ms_device, r.gbs, r.flags) for r in arr[:n]]
+                            r.first_bad_word, r.bytes, r.ms_event, r.ms_device, r.gbs, r.flags, r.gbs_ref, r.frac,
+                            r.min_gbs_applied) for r in arr[:n]]
 
     def probe_inject_fault(self, device: int, word_index: int, mask: int):
         N.check(N.lib.b2dp_probe_inject_fault(self._h, device, word_index, mask), self._h)
 
     def probe_reset(self, device: int = -1):
         N.check(N.lib.b2dp_probe_reset(self._h, device), self._h)
+
+    def probe_set_ref(self, device: int = -1, gbs_ref: float = 0.0):
+        """Pin the bandwidth ceiling the fractional floor refers to (<= 0: back to the device's own calibration)."""
+        N.check(N.lib.b2dp_probe_set_ref(self._h, device, gbs_ref), self._h)
 
     def probe_peek(self, device: int, word_index: int, n_words: int):
         import numpy as np
@@ -174,7 +184,7 @@ class Context:
         del keep
         stats = CycleStats(st.n_devices, st.n_unhealthy, bool(st.homogeneous), bool(st.node_healthy), st.ms_total,
                            st.ms_enumerate, st.ms_probe, st.ms_encode, st.probe_gbs_min, st.probe_gbs_sum,
-                           st.probe_bytes, st.ms_link_check, st.n_link_faults)
+                           st.probe_bytes, st.ms_link_check, st.n_link_faults, st.probe_ms_device_max, st.probe_frac_min)
         return wire, stats
 
     def watch(self, callback, resource: str = "gpu", pulse_ms: int = 0, flags: int = 0, timeout_ms=0, min_gbs=0.0):
@@ -201,6 +211,23 @@ class Context:
     def start(self) -> int:
         """plugin.go:82-91 Start(); returns the allocator-init rc (0 ok) without raising."""
         return N.lib.b2dp_start(self._h)
+
+    def pair_weights(self):
+        """p2pWeights of the context's own allocator as {from: {to: weight}} (device.go:220-252); needs start()."""
+        cap = 4096
+        while True:
+            arr = (N.PairWeight * cap)()
+            n, rows = C.c_int(0), C.c_int(0)
+            rc = N.lib.b2dp_pair_weights(self._h, arr, cap, C.byref(n), C.byref(rows))
+            if rc == N.E_NOSPC:
+                cap = n.value
+                continue
+            N.check(rc, self._h)
+            break
+        w = {}
+        for e in arr[:n.value]:
+            w.setdefault(e.node_from, {})[e.node_to] = e.weight
+        return w
 
     def preferred_allocation_available(self) -> bool:
         v = C.c_int32()
@@ -252,7 +279,7 @@ class Watch:
             s = st.contents
             stats = CycleStats(s.n_devices, s.n_unhealthy, bool(s.homogeneous), bool(s.node_healthy), s.ms_total,
                                s.ms_enumerate, s.ms_probe, s.ms_encode, s.probe_gbs_min, s.probe_gbs_sum, s.probe_bytes,
-                               s.ms_link_check, s.n_link_faults)
+                               s.ms_link_check, s.n_link_faults, s.probe_ms_device_max, s.probe_frac_min)
             callback(rc, bytes(buf[:ln]) if ln else b"", stats)
         self._cb = N.WatchCb(tramp)          # keep the trampoline alive as long as the loop
         self._h = C.c_void_p()

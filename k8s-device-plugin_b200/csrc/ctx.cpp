@@ -14,6 +14,7 @@
 
 #include "gosem.hpp"
 #include "internal.hpp"
+#include "pattern_math.hpp"
 #include "pbwire.hpp"
 
 using namespace b2dp;
@@ -42,6 +43,7 @@ struct b2dp_ctx {
     std::vector<Device> stream_devs;  // the device list of the current ListAndWatch stream
     bool have_stream_devs = false;
     std::string cdi_kind;             // cuda: optional CDI kind ("nvidia.com/gpu"): Allocate also names CDI devices
+    bool ids_by_index = false;        // cuda: id_strategy=index -- NVML indices instead of UUIDs in NVIDIA_VISIBLE_DEVICES / CDI names
     std::string owned_tmp_root;       // synthetic: backend -- the generated tree, removed at close
     std::vector<b2dp_watch*> watches;  // running b2dp_watch loops (guarded by mu): a latched Xid beats them all at once
 };
@@ -165,8 +167,14 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         if (!parse_kv(u.substr(5), kv)) return fail(B2DP_E_INVAL, "bad cuda: uri");
         CudaConfig cfg;
         std::string cdi_kind;
+        bool ids_by_index = false;
         for (auto& p : kv) {
             if (p.first == "cdi") { cdi_kind = p.second; continue; }
+            if (p.first == "id_strategy") {
+                if (p.second == "index") ids_by_index = true;
+                else if (p.second != "uuid") return fail(B2DP_E_INVAL, "id_strategy= wants uuid|index");
+                continue;
+            }
             if (p.first == "devices") {
                 size_t pos = 0;
                 while (pos <= p.second.size()) {
@@ -179,6 +187,9 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else if (p.first == "slots") cfg.slots = atoi(p.second.c_str());
             else if (p.first == "p2p_bytes") cfg.p2p_bytes = strtoull(p.second.c_str(), nullptr, 0);
             else if (p.first == "min_gbs") cfg.min_gbs = (float)atof(p.second.c_str());
+            else if (p.first == "min_frac") cfg.min_frac = (float)atof(p.second.c_str());
+            else if (p.first == "ref_gbs") cfg.ref_gbs = (float)atof(p.second.c_str());
+            else if (p.first == "calib") cfg.calib = atoi(p.second.c_str());
             else if (p.first == "sysroot") cfg.sysroot = p.second;
             else if (p.first == "busy") {
                 if (p.second == "probe") cfg.busy_policy = 0;
@@ -201,6 +212,8 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         }
         if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");
         if (cfg.slots < 2 || cfg.slots > 4096) return fail(B2DP_E_INVAL, "slots must be in [2, 4096]");
+        if (!(cfg.min_frac >= 0.f && cfg.min_frac <= 1.f)) return fail(B2DP_E_INVAL, "min_frac must be in [0, 1]");
+        if (cfg.calib < 0 || cfg.calib > 64) return fail(B2DP_E_INVAL, "calib must be in [0, 64]");
         std::string err;
         CudaBackend* be = nullptr;
         int rc = cuda_backend_open(cfg, &be, err);
@@ -210,6 +223,7 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         c->sysroot = cfg.sysroot;
         c->cuda = be;
         c->cdi_kind = cdi_kind;
+        c->ids_by_index = ids_by_index;
         // xid=1: a device-level Xid is pushed to the kubelet at once -- every running ListAndWatch loop of this
         // context runs a heartbeat cycle now instead of at the next pulse (the reference only learns at a pulse)
         cuda_set_health_event_callback(be, [c] {
@@ -334,6 +348,18 @@ extern "C" int b2dp_probe_reset(b2dp_ctx* c, int device) {
     int rc = cuda_probe_reset(c->cuda, device, err);
     return rc == B2DP_OK ? rc : fail(rc, err);
 }
+extern "C" int b2dp_probe_set_ref(b2dp_ctx* c, int device, float gbs_ref) {
+    if (!c) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "cuda: backend only");
+    std::string err;
+    int rc = cuda_set_ref(c->cuda, device, gbs_ref, err);
+    return rc == B2DP_OK ? rc : fail(rc, err);
+}
+extern "C" int b2dp_expected_checksum(uint64_t n_words, uint32_t seed, uint64_t* checksum) {
+    if (!checksum) return B2DP_E_INVAL;
+    *checksum = expected_checksum_host(n_words, seed);
+    return B2DP_OK;
+}
 extern "C" int b2dp_probe_peek(b2dp_ctx* c, int device, uint64_t word_index, uint32_t* out, uint64_t n_words) {
     if (!c || (!out && n_words)) return B2DP_E_INVAL;
     if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "cuda: backend only");
@@ -419,13 +445,17 @@ extern "C" int b2dp_list_and_watch(b2dp_ctx* c, const char* resource, const b2dp
             // the probe answers per enumerated device (same order as devs)
             have_source = true;
             st.probe_gbs_min = 1e30f;
+            st.probe_frac_min = 1e30f;
             for (auto& r : res) {
                 if (r.device >= 0 && r.device < (int)devs.size()) hmap[devs[r.device].id] = r.healthy;
                 st.probe_bytes += r.bytes;
                 st.probe_gbs_sum += r.gbs;
                 if (r.gbs < st.probe_gbs_min) st.probe_gbs_min = r.gbs;
+                if (r.ms_device > st.probe_ms_device_max) st.probe_ms_device_max = r.ms_device;
+                if (r.gbs_ref > 0 && r.frac < st.probe_frac_min) st.probe_frac_min = r.frac;
             }
             if (res.empty()) st.probe_gbs_min = 0;
+            if (st.probe_frac_min > 1e29f) st.probe_frac_min = 0;
             if ((flags & B2DP_LW_LINK_CHECK) && devs.size() > 1) {
                 // optional: re-measure the NVLink matrix (both directions at once, one timed pass per
                 // pair) and fail a device whose link to any peer delivers corrupt data or has dropped
@@ -636,17 +666,19 @@ extern "C" int b2dp_allocate_response(b2dp_ctx* c, const char* const* ids, int n
     int rc = device_specs(c, ids, n_ids, specs);
     if (rc != B2DP_OK) return rc;
     std::string wire;
+    // The reference's Allocate sets no envs (plugin.go:356-393).  On NVIDIA nodes the container runtime hook selects
+    // GPUs from NVIDIA_VISIBLE_DEVICES, so the cuda backend also names the allocated devices there (envs = field 1,
+    // map<string,string>) -- by UUID (or NVML index with id_strategy=index), never by /dev/nvidia minor: the runtime
+    // reads a bare integer as an NVML index, and minors differ from indices on HGX boards.
+    std::vector<std::string> rt_ids;
     if (c->kind == b2dp_ctx::CUDA) {
-        // The reference's Allocate sets no envs (plugin.go:356-393).  On NVIDIA nodes the container
-        // runtime hook selects GPUs from NVIDIA_VISIBLE_DEVICES, so the cuda backend also names the
-        // allocated devices there (envs = field 1, map<string,string>).
-        std::vector<Device> devs;
-        rc = enumerate_ctx(c, devs);
-        if (rc != B2DP_OK) return rc;
+        for (int i = 0; i < n_ids; ++i) {
+            if (!ids[i]) continue;
+            const std::string rid = cuda_runtime_id(c->cuda, ids[i], c->ids_by_index);
+            if (!rid.empty()) rt_ids.push_back(rid);
+        }
         std::string list;
-        for (int i = 0; i < n_ids; ++i)
-            for (const auto& d : devs)
-                if (ids[i] && d.id == ids[i]) { list += (list.empty() ? "" : ",") + std::to_string(d.card); break; }
+        for (auto& r : rt_ids) list += (list.empty() ? "" : ",") + r;
         std::string entry;
         pb::string_field(entry, 1, "NVIDIA_VISIBLE_DEVICES");
         pb::string_field(entry, 2, list.empty() ? "void" : list);
@@ -654,19 +686,13 @@ extern "C" int b2dp_allocate_response(b2dp_ctx* c, const char* const* ids, int n
     }
     for (auto& s : specs) pb::encode_devspec(wire, 3, s.container_path, s.host_path, s.permissions);
     if (c->kind == b2dp_ctx::CUDA && !c->cdi_kind.empty()) {
-        // cdi=<kind>: ContainerAllocateResponse.cdi_devices (field 5, CDIDevice{name=1}) = "<kind>=<minor>", the
+        // cdi=<kind>: ContainerAllocateResponse.cdi_devices (field 5, CDIDevice{name=1}) = "<kind>=<uuid|index>", the
         // fully qualified names of an nvidia-ctk generated CDI spec; a CDI-enabled runtime injects from those
-        std::vector<Device> devs;
-        rc = enumerate_ctx(c, devs);
-        if (rc != B2DP_OK) return rc;
-        for (int i = 0; i < n_ids; ++i)
-            for (const auto& d : devs)
-                if (ids[i] && d.id == ids[i]) {
-                    std::string cdi;
-                    pb::string_field(cdi, 1, c->cdi_kind + "=" + std::to_string(d.card));
-                    pb::bytes_field(wire, 5, cdi);
-                    break;
-                }
+        for (auto& r : rt_ids) {
+            std::string cdi;
+            pb::string_field(cdi, 1, c->cdi_kind + "=" + r);
+            pb::bytes_field(wire, 5, cdi);
+        }
     }
     *len = wire.size();
     if (wire.size() > cap) return B2DP_E_NOSPC;
@@ -710,6 +736,25 @@ extern "C" int b2dp_start(b2dp_ctx* c) {
     c->allocator_init_error = rc != B2DP_OK;  // plugin.go:86-90
     if (rc != B2DP_OK && t_last_error.empty()) t_last_error = b2dp_strerror(rc);
     return rc;
+}
+
+extern "C" int b2dp_pair_weights(b2dp_ctx* c, b2dp_pair_weight* out, int cap, int* n, int* n_rows) {
+    if (!c || !n || cap < 0) return B2DP_E_INVAL;
+    std::shared_ptr<BestEffortPolicy> p;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        p = c->policy;
+    }
+    if (!p) return fail(B2DP_E_ALLOC_INIT, b2dp_strerror(B2DP_E_ALLOC_INIT));
+    std::vector<b2dp_pair_weight> w;
+    int rows = 0;
+    policy_pair_weights(p.get(), w, &rows);
+    *n = (int)w.size();
+    if (n_rows) *n_rows = rows;
+    if (*n > cap) return B2DP_E_NOSPC;
+    if (*n && !out) return B2DP_E_INVAL;
+    memcpy(out, w.data(), w.size() * sizeof(b2dp_pair_weight));
+    return B2DP_OK;
 }
 
 extern "C" int b2dp_preferred_allocation_available(b2dp_ctx* c, int32_t* available) {
@@ -974,6 +1019,14 @@ extern "C" int b2dp_export_kfd_tree(b2dp_ctx* c, const char* dir_c) {
         ok &= write_file(drm + "/product_name", (i < src.product_name.size() ? src.product_name[i] : "") + "\n");
         ok &= write_file(drm + "/driver/module/version", src.driver_version + "\n");
         ok &= write_file(drm + "/driver/module/srcversion", src.driver_src_version + "\n");
+        // what the reference reads through libdrm ioctls (family, per-block firmware versions) has no sysfs file; the
+        // export carries it as two side files the kfd: backend and the oracle's drm provider read back
+        if (i < src.family.size() && !src.family[i].empty()) ok &= write_file(drm + "/b2dp_family", src.family[i] + "\n");
+        if (i < src.firmware.size() && !src.firmware[i].empty()) {
+            std::string fw;
+            for (const auto& bv : src.firmware[i]) fw += bv.first + " " + bv.second + "\n";
+            ok &= write_file(drm + "/b2dp_firmware", fw);
+        }
     }
     ok &= mkdirs(dir + "/sys/devices/platform");
     return ok ? B2DP_OK : fail(B2DP_E_IO, "failed writing the kfd tree under " + dir);

@@ -29,6 +29,7 @@
 #include "gosem.hpp"
 #include "hbm_probe.cuh"
 #include "internal.hpp"
+#include "pattern_math.hpp"
 
 namespace b2dp {
 
@@ -39,6 +40,7 @@ constexpr int kTmaStages = 3;
 constexpr int kTmaCtasPerSm = 2;    // 2 x 3 x 16 KiB = 96 KiB staged per SM
 constexpr size_t kTmaSmem = (size_t)kTmaStages * kTmaTileVec * 16 + 2 * kTmaStages * 8;
 constexpr int kRegThreads = 512, kRegUnroll = 2, kRegCtasPerSm = 2;
+constexpr unsigned long long kFloorMinBytes = 128ull << 20;  // a ring slot above the 126 MB L2: the pass measures HBM, not the cache
 
 // bit b of (uint32(i) * K) summed over i < n_words, for the closed-form checksum
 __global__ void pattern_bit_counts(unsigned long long n_words, unsigned long long* counts /*[32]*/) {
@@ -78,13 +80,20 @@ struct Nvml {
     int (*event_wait)(void*, EventData*, unsigned) = nullptr;          // nvmlEventSetWait_v2
     int (*event_set_free)(void*) = nullptr;
     int (*shutdown)() = nullptr;
+    int (*index_of)(void*, unsigned*) = nullptr;                       // nvmlDeviceGetIndex
+    int (*uuid_of)(void*, char*, unsigned) = nullptr;                  // nvmlDeviceGetUUID
+    int (*inforom_image)(void*, char*, unsigned) = nullptr;            // nvmlDeviceGetInforomImageVersion
+    int (*inforom_object)(void*, int, char*, unsigned) = nullptr;      // nvmlDeviceGetInforomVersion(OEM 0 / ECC 1 / POWER 2)
+    int (*gsp_firmware)(void*, char*) = nullptr;                       // nvmlDeviceGetGspFirmwareVersion
     bool ok = false;
     ~Nvml() {
         if (ok && shutdown) shutdown();  // nvmlInit/nvmlShutdown are reference counted
         if (lib) dlclose(lib);
     }
     void load() {
-        lib = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+        // B2DP_NVML_LIBRARY: an alternative NVML (tests: tests/native/nvml_stub.cpp describes a MIG-partitioned node)
+        const char* alt = getenv("B2DP_NVML_LIBRARY");
+        lib = dlopen(alt && *alt ? alt : "libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
         if (!lib) return;
         init = (int (*)())dlsym(lib, "nvmlInit_v2");
         shutdown = (int (*)())dlsym(lib, "nvmlShutdown");
@@ -100,6 +109,11 @@ struct Nvml {
         register_events = (int (*)(void*, unsigned long long, void*))dlsym(lib, "nvmlDeviceRegisterEvents");
         event_wait = (int (*)(void*, EventData*, unsigned))dlsym(lib, "nvmlEventSetWait_v2");
         event_set_free = (int (*)(void*))dlsym(lib, "nvmlEventSetFree");
+        index_of = (int (*)(void*, unsigned*))dlsym(lib, "nvmlDeviceGetIndex");
+        uuid_of = (int (*)(void*, char*, unsigned))dlsym(lib, "nvmlDeviceGetUUID");
+        inforom_image = (int (*)(void*, char*, unsigned))dlsym(lib, "nvmlDeviceGetInforomImageVersion");
+        inforom_object = (int (*)(void*, int, char*, unsigned))dlsym(lib, "nvmlDeviceGetInforomVersion");
+        gsp_firmware = (int (*)(void*, char*))dlsym(lib, "nvmlDeviceGetGspFirmwareVersion");
         ok = init && init() == 0;
     }
 };
@@ -120,8 +134,14 @@ struct Gpu {
     int ordinal = 0;
     Device dev;                 // the enumerate record
     std::string name, pci_device_id, vbios, family;
+    std::string uuid;                     // "GPU-xxxxxxxx-xxxx-xxxx-xxxx-xxxxxxxxxxxx" (cudaDeviceProp.uuid == nvmlDeviceGetUUID)
+    int nvml_index = -1;                  // nvmlDeviceGetIndex: what a bare integer in NVIDIA_VISIBLE_DEVICES / a CDI name means
+    std::string inforom_image, inforom_oem, inforom_ecc, inforom_power, gsp_fw;
     int64_t vram = 0, sms = 0;
     bool mig_capable = false;
+    float gbs_cal = 0.f;                  // best of the calibration passes at open (this device)
+    std::atomic<float> gbs_ref{0.f};      // the ceiling the GB/s floor is a fraction of (peer group max, ref_gbs=, or b2dp_probe_set_ref)
+    std::array<unsigned long long, 32> bc{};  // host closed-form bit counts for n_vec*4 words (pattern_math.hpp)
     void* nvh = nullptr;                  // NVML device handle (optional)
     unsigned long long ecc_base = 0;      // uncorrected volatile ECC count when the context was opened
     bool have_ecc = false;
@@ -205,44 +225,96 @@ static std::shared_ptr<Completion> post(Gpu* g, std::function<void()> fn) {
 template <class F>
 static void run_sync(Gpu* g, F&& fn) { post(g, std::forward<F>(fn))->wait(); }
 
-// closed-form checksum of a clean buffer of n_words with `seed`
-static unsigned long long expected_checksum(const std::array<unsigned long long, 32>& c, unsigned long long n_words,
-                                            uint32_t seed) {
-    unsigned long long s = 0;
-    for (int b = 0; b < 32; ++b) {
-        const unsigned long long ones = ((seed >> b) & 1u) ? n_words - c[b] : c[b];
-        s += ones << b;
-    }
-    return s;
-}
-
-static int get_bitcounts(CudaBackend* be, unsigned long long n_words, std::array<unsigned long long, 32>& out,
-                         std::string& err) {
+// Closed-form checksum of a clean buffer: computed on the HOST (pattern_math.hpp) -- a health probe must not ask the
+// device under test for its own reference value.  Cached per size; the per-GPU ring size is cached in Gpu::bc.
+static const std::array<unsigned long long, 32>& host_bitcounts(CudaBackend* be, unsigned long long n_words) {
     std::lock_guard<std::mutex> l(be->bc_mu);
     auto it = be->bitcounts.find(n_words);
-    if (it != be->bitcounts.end()) { out = it->second; return B2DP_OK; }
-    Gpu* g = be->gpus[0].get();
-    cudaError_t ce = cudaSuccess;
-    std::array<unsigned long long, 32> host{};
-    run_sync(g, [&] {
-        unsigned long long* d = nullptr;
-        if ((ce = cudaMalloc(&d, 32 * sizeof(unsigned long long))) != cudaSuccess) return;
-        cudaMemsetAsync(d, 0, 32 * sizeof(unsigned long long), g->stream);
-        pattern_bit_counts<<<(int)g->sms * 4, 256, 0, g->stream>>>(n_words, d);
-        ce = cudaMemcpyAsync(host.data(), d, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(g->stream);
-        cudaFree(d);
-    });
-    if (ce != cudaSuccess) { err = cuda_err("pattern_bit_counts", ce); return B2DP_E_CUDA; }
-    be->bitcounts[n_words] = host;
-    out = host;
-    return B2DP_OK;
+    if (it == be->bitcounts.end()) it = be->bitcounts.emplace(n_words, pattern_bit_counts_host(n_words)).first;
+    return it->second;  // std::map nodes are stable
 }
 
 static std::string read_trim(const std::string& p) {
     std::string d;
     if (!go::read_file(p, d)) return "";
     return go::trim_space(d);
+}
+
+// ---- the probe fan-out -----------------------------------------------------------------------
+struct ProbeJobResult {
+    cudaError_t ce = cudaSuccess;
+    ProbeOut out{};
+    float ms = 0;
+    uint32_t seed = 0;
+    unsigned long long seq = 0;
+    bool seq_ok = false;
+    unsigned long long n_vec = 0;   // vectors this pass covers (shrunk on a busy GPU)
+    bool advance = true;            // false: verify-only prefix pass, buffers/seed stay as they are
+    bool timed = false;             // bracket the kernel with CUDA events (B2DP_PROBE_EVENT_TIMING)
+    int grid = 0;                   // CTAs to launch (0 = the tuned shape); diagnostic hook, see b2dp_probe_opts.grid_ctas
+};
+
+static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uint32_t seed, uint32_t delta,
+                         const uint4* src, uint4* dst, unsigned long long seq, int grid = 0) {
+    if (variant == B2DP_PROBE_VARIANT_R128)
+        hbm_probe_r128<kRegThreads, kRegUnroll><<<grid > 0 ? grid : (int)g->sms * kRegCtasPerSm, kRegThreads, 0, g->stream>>>(
+            src, dst, n_vec, seed, delta, g->ctl, g->out_d, seq);
+    else
+        hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>
+            <<<grid > 0 ? grid : (int)g->sms * kTmaCtasPerSm, (kTmaCW + 1) * 32, kTmaSmem, g->stream>>>(
+                src, dst, n_vec, seed, delta, g->ctl, g->out_d, seq);
+}
+
+// Enqueue one pass on g's stream (caller must have made g's device current).
+static void probe_issue(Gpu* g, ProbeJobResult* r, uint32_t variant) {
+    const uint32_t seed = g->seed, next = seed * 1664525u + 1013904223u;
+    const unsigned long long n_vec = r->n_vec ? r->n_vec : g->n_vec;
+    r->n_vec = n_vec;
+    r->seed = seed;
+    r->seq = ++g->seq;
+    if (r->timed) cudaEventRecord(g->e0, g->stream);
+    launch_probe(g, n_vec, variant, seed, r->advance ? seed ^ next : 0u, g->buf[g->cur], g->buf[g->next()], r->seq, r->grid);
+    r->ce = cudaGetLastError();
+    if (r->timed) cudaEventRecord(g->e1, g->stream);
+}
+
+// The last CTA publishes the result block and, after a system-scope fence, the launch's sequence
+// number into pinned host memory (hbm_probe.cuh finish()): seeing the number means every CTA's
+// stores and the whole block are done -- completion without a driver call.
+static inline bool probe_published(const Gpu* g, const ProbeJobResult* r) {
+    return *(volatile const unsigned long long*)&g->out_h->seq == r->seq;
+}
+
+// After the pass completed: read the published result, advance the seed / ping-pong state.
+static void probe_collect(Gpu* g, ProbeJobResult* r) {
+    const unsigned long long n_vec = g->n_vec;  // repairs re-fill the whole slot
+    cudaError_t e = r->ce;
+    if (e == cudaSuccess && r->timed) {
+        e = cudaEventSynchronize(g->e1);  // the result is already published; the event follows within ~1 us
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&r->ms, g->e0, g->e1);
+    }
+    r->ce = e;
+    if (e != cudaSuccess) return;
+    std::atomic_thread_fence(std::memory_order_acquire);       // the sequence number was read first (probe_published)
+    memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // the block is complete once its sequence number shows
+    r->seq_ok = r->out.seq == r->seq;
+    if (!r->advance) {
+        if (r->out.mismatches != 0 || !r->seq_ok) {  // repair the source buffer in place
+            cudaSetDevice(g->ordinal);
+            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
+            cudaStreamSynchronize(g->stream);
+        }
+        return;
+    }
+    g->seed = g->seed * 1664525u + 1013904223u;
+    g->cur = g->next();
+    if (r->out.mismatches != 0 || !r->seq_ok) {
+        // report once, then start the next pass from a clean pattern: a transient flip is
+        // reported exactly once, a stuck cell shows up again on the next pass
+        cudaSetDevice(g->ordinal);
+        hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
+        cudaStreamSynchronize(g->stream);
+    }
 }
 
 static void xid_listener(CudaBackend* be);
@@ -289,6 +361,13 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         snprintf(devid, sizeof devid, "%04x:%02x:%02x:0", prop.pciDomainID, prop.pciBusID, prop.pciDeviceID);  // amdgpu.go:141
         g->dev.dev_id = devid;
         g->name = prop.name;
+        {
+            const unsigned char* u = reinterpret_cast<const unsigned char*>(prop.uuid.bytes);
+            char ub[48];
+            snprintf(ub, sizeof ub, "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", u[0], u[1], u[2],
+                     u[3], u[4], u[5], u[6], u[7], u[8], u[9], u[10], u[11], u[12], u[13], u[14], u[15]);
+            g->uuid = ub;
+        }
         g->vram = (int64_t)prop.totalGlobalMem;
         g->sms = prop.multiProcessorCount;
         g->family = prop.major == 10 || prop.major == 12 ? "Blackwell" : prop.major == 9 ? "Hopper"
@@ -312,8 +391,19 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
                     g->have_ecc = true;
                 unsigned mn = 0;
                 if (be->nvml.minor_number(h, &mn) == 0) { g->dev.card = (int)mn; have_minor = true; }
-                char vb[64] = {0};
+                char vb[96] = {0};
                 if (be->nvml.vbios && be->nvml.vbios(h, vb, sizeof vb) == 0) g->vbios = vb;
+                unsigned ni = 0;
+                if (be->nvml.index_of && be->nvml.index_of(h, &ni) == 0) g->nvml_index = (int)ni;
+                if (be->nvml.uuid_of && be->nvml.uuid_of(h, vb, sizeof vb) == 0 && vb[0]) g->uuid = vb;
+                // firmware label sources (the analogue of libdrm's per-block firmware versions, amdgpu.go:392-437)
+                if (be->nvml.inforom_image && be->nvml.inforom_image(h, vb, sizeof vb) == 0) g->inforom_image = vb;
+                if (be->nvml.inforom_object) {
+                    if (be->nvml.inforom_object(h, 0, vb, sizeof vb) == 0) g->inforom_oem = vb;
+                    if (be->nvml.inforom_object(h, 1, vb, sizeof vb) == 0) g->inforom_ecc = vb;
+                    if (be->nvml.inforom_object(h, 2, vb, sizeof vb) == 0) g->inforom_power = vb;
+                }
+                if (be->nvml.gsp_firmware && be->nvml.gsp_firmware(h, vb) == 0) g->gsp_fw = vb;  // NVML_GSP_FIRMWARE_VERSION_BUF_SIZE = 64
                 unsigned cur = 0, pend = 0;
                 if (be->nvml.mig_mode && be->nvml.mig_mode(h, &cur, &pend) == 0) g->mig_capable = true;
             }
@@ -352,9 +442,10 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         Gpu* g = be->gpus[i].get();
         const unsigned long long bytes = cfg.bytes, n_vec = cfg.bytes / 16;
         const int idx = (int)i;
+        const int calib = cfg.calib;
         g->buf.assign((size_t)cfg.slots, nullptr);
         (void)n_vec;
-        cs.push_back(post(g, [g, bytes, idx, &errs, &where] {
+        cs.push_back(post(g, [g, bytes, idx, calib, &errs, &where] {
             cudaError_t e;
 #define TRY(x) if ((e = (x)) != cudaSuccess) { errs[idx] = e; where[idx] = #x; return; }
             TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
@@ -390,6 +481,35 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
             hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[0], g->n_vec, g->seed);
             TRY(cudaGetLastError());
             TRY(cudaStreamSynchronize(g->stream));
+            // Integer self-test of THIS GPU against the host: the pattern's bit counts, computed by the SMs, must equal
+            // the host's closed form (which is what every later verdict is judged against).
+            g->bc = pattern_bit_counts_host(g->n_vec * 4);
+            {
+                unsigned long long* d = nullptr;
+                std::array<unsigned long long, 32> dev_counts{};
+                TRY(cudaMalloc(&d, sizeof dev_counts));
+                TRY(cudaMemsetAsync(d, 0, sizeof dev_counts, g->stream));
+                pattern_bit_counts<<<(int)g->sms * 4, 256, 0, g->stream>>>(g->n_vec * 4, d);
+                TRY(cudaGetLastError());
+                TRY(cudaMemcpyAsync(dev_counts.data(), d, sizeof dev_counts, cudaMemcpyDeviceToHost, g->stream));
+                TRY(cudaStreamSynchronize(g->stream));
+                cudaFree(d);
+                if (dev_counts != g->bc) { errs[idx] = cudaErrorUnknown; where[idx] = "integer self-test (pattern bit counts != host closed form)"; return; }
+            }
+            // Calibration: best of `calib` warm, non-advancing passes (read slot 0, write slot 1 un-re-keyed; seed and
+            // ring position stay where they are) = what this device streams when healthy and idle.
+            for (int k = 0; k < calib + 1; ++k) {
+                ProbeJobResult r;
+                r.advance = false;
+                r.timed = true;
+                probe_issue(g, &r, 0u);
+                if (r.ce == cudaSuccess) r.ce = cudaStreamSynchronize(g->stream);
+                probe_collect(g, &r);
+                TRY(r.ce);
+                if (k == 0 || r.ms <= 0) continue;  // first pass warms clocks, TLBs and the instruction cache
+                const float gbs = (float)(2.0 * (double)g->n_vec * 16.0 / (double)r.ms * 1e-6);
+                if (gbs > g->gbs_cal) g->gbs_cal = gbs;
+            }
 #undef TRY
         }));
     }
@@ -412,6 +532,17 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         CudaBackend* raw = be.release();
         cuda_backend_close(raw);
         return B2DP_E_CUDA;
+    }
+    // The ceiling a device's GB/s floor is a fraction of: ref_gbs= if given, else the best calibration of any
+    // device of the same product with the same ring size -- a part that is already slow when the daemon starts is
+    // judged against its siblings, not against itself.
+    for (auto& g : be->gpus) {
+        if (g->broken) continue;
+        float ref = cfg.ref_gbs;
+        if (ref <= 0)
+            for (auto& o : be->gpus)
+                if (!o->broken && o->name == g->name && o->n_vec == g->n_vec) ref = std::max(ref, o->gbs_cal);
+        g->gbs_ref.store(ref);
     }
     *out = be.release();
     return B2DP_OK;
@@ -473,85 +604,20 @@ void cuda_label_source(CudaBackend* be, LabelSource& src) {
         src.product_name.push_back(g->name);
         src.device_id.push_back(g->pci_device_id);
         src.vbios.push_back(g->vbios);
+        // per-block firmware versions, the key scheme of main.go:116-144 ("<block>.fw.<version>")
+        std::vector<std::pair<std::string, std::string>> fw;
+        if (!g->vbios.empty()) fw.push_back({"vbios", g->vbios});
+        if (!g->inforom_image.empty()) fw.push_back({"inforom-img", g->inforom_image});
+        if (!g->inforom_oem.empty()) fw.push_back({"inforom-oem", g->inforom_oem});
+        if (!g->inforom_ecc.empty()) fw.push_back({"inforom-ecc", g->inforom_ecc});
+        if (!g->inforom_power.empty()) fw.push_back({"inforom-pwr", g->inforom_power});
+        if (!g->gsp_fw.empty()) fw.push_back({"gsp", g->gsp_fw});
+        src.firmware.push_back(std::move(fw));
         src.vram_bytes.push_back(g->vram);
         src.sm_count.push_back(g->sms);
         mig = mig && g->mig_capable;
     }
     src.part_supported[0] = src.part_supported[1] = mig;
-}
-
-// ---- the probe fan-out -----------------------------------------------------------------------
-struct ProbeJobResult {
-    cudaError_t ce = cudaSuccess;
-    ProbeOut out{};
-    float ms = 0;
-    uint32_t seed = 0;
-    unsigned long long seq = 0;
-    bool seq_ok = false;
-    unsigned long long n_vec = 0;   // vectors this pass covers (shrunk on a busy GPU)
-    bool advance = true;            // false: verify-only prefix pass, buffers/seed stay as they are
-    bool timed = false;             // bracket the kernel with CUDA events (B2DP_PROBE_EVENT_TIMING)
-};
-
-static void launch_probe(Gpu* g, unsigned long long n_vec, uint32_t variant, uint32_t seed, uint32_t delta,
-                         const uint4* src, uint4* dst, unsigned long long seq) {
-    if (variant == B2DP_PROBE_VARIANT_R128)
-        hbm_probe_r128<kRegThreads, kRegUnroll><<<(int)g->sms * kRegCtasPerSm, kRegThreads, 0, g->stream>>>(
-            src, dst, n_vec, seed, delta, g->ctl, g->out_d, seq);
-    else
-        hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>
-            <<<(int)g->sms * kTmaCtasPerSm, (kTmaCW + 1) * 32, kTmaSmem, g->stream>>>(src, dst, n_vec, seed, delta,
-                                                                                    g->ctl, g->out_d, seq);
-}
-
-// Enqueue one pass on g's stream (caller must have made g's device current).
-static void probe_issue(Gpu* g, ProbeJobResult* r, uint32_t variant) {
-    const uint32_t seed = g->seed, next = seed * 1664525u + 1013904223u;
-    const unsigned long long n_vec = r->n_vec ? r->n_vec : g->n_vec;
-    r->n_vec = n_vec;
-    r->seed = seed;
-    r->seq = ++g->seq;
-    if (r->timed) cudaEventRecord(g->e0, g->stream);
-    launch_probe(g, n_vec, variant, seed, r->advance ? seed ^ next : 0u, g->buf[g->cur], g->buf[g->next()], r->seq);
-    r->ce = cudaGetLastError();
-    if (r->timed) cudaEventRecord(g->e1, g->stream);
-}
-
-// The last CTA publishes the result block and, after a system-scope fence, the launch's sequence
-// number into pinned host memory (hbm_probe.cuh finish()): seeing the number means every CTA's
-// stores and the whole block are done -- completion without a driver call.
-static inline bool probe_published(const Gpu* g, const ProbeJobResult* r) {
-    return *(volatile const unsigned long long*)&g->out_h->seq == r->seq;
-}
-
-// After the pass completed: read the published result, advance the seed / ping-pong state.
-static void probe_collect(Gpu* g, ProbeJobResult* r) {
-    const unsigned long long n_vec = g->n_vec;  // repairs re-fill the whole slot
-    cudaError_t e = r->ce;
-    if (e == cudaSuccess && r->timed) {
-        e = cudaEventSynchronize(g->e1);  // the result is already published; the event follows within ~1 us
-        if (e == cudaSuccess) e = cudaEventElapsedTime(&r->ms, g->e0, g->e1);
-    }
-    r->ce = e;
-    if (e != cudaSuccess) return;
-    std::atomic_thread_fence(std::memory_order_acquire);       // the sequence number was read first (probe_published)
-    memcpy(&r->out, (const void*)g->out_h, sizeof(ProbeOut));  // the block is complete once its sequence number shows
-    r->seq_ok = r->out.seq == r->seq;
-    if (!r->advance) {
-        if (r->out.mismatches != 0 || !r->seq_ok) {  // repair the source buffer in place
-            hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
-            cudaStreamSynchronize(g->stream);
-        }
-        return;
-    }
-    g->seed = g->seed * 1664525u + 1013904223u;
-    g->cur = g->next();
-    if (r->out.mismatches != 0 || !r->seq_ok) {
-        // report once, then start the next pass from a clean pattern: a transient flip is
-        // reported exactly once, a stuck cell shows up again on the next pass
-        hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
-        cudaStreamSynchronize(g->stream);
-    }
 }
 
 // Xids that report an application's own fault (bad kernel, MMU fault of a user context, preemption,
@@ -590,13 +656,16 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     const bool via_workers = opts && (opts->flags & B2DP_PROBE_VIA_WORKERS);
     const bool timed = opts && (opts->flags & B2DP_PROBE_EVENT_TIMING);
     const uint32_t timeout_ms = opts && opts->timeout_ms ? opts->timeout_ms : 5000;  // health.go:37
-    const float min_gbs = opts && opts->min_gbs > 0 ? opts->min_gbs : be->cfg.min_gbs;
+    // GB/s floor: an absolute one if the call or the context names it (min_gbs), else min_frac (default 0.8,
+    // BASELINE.json's ">= 80 % of HBM peak") of the device's calibrated ceiling
+    const float abs_floor = opts && opts->min_gbs > 0 ? opts->min_gbs : be->cfg.min_gbs;
+    const int grid = opts ? (int)opts->grid_ctas : 0;
     const size_t n = be->gpus.size();
     std::vector<std::shared_ptr<ProbeJobResult>> res(n);
     std::vector<std::shared_ptr<Completion>> cs(n);
     std::vector<char> state(n, 0);  // 0 pending, 1 done, 2 timed out / busy
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
-    for (size_t i = 0; i < n; ++i) { res[i] = std::make_shared<ProbeJobResult>(); res[i]->timed = timed; }
+    for (size_t i = 0; i < n; ++i) { res[i] = std::make_shared<ProbeJobResult>(); res[i]->timed = timed; res[i]->grid = grid; }
     for (size_t i = 0; i < n; ++i) if (be->gpus[i]->broken) state[i] = 4;  // never launched on
     // busy policy (tenant workloads): a 2 GiB-traffic probe steals bandwidth from a pod that owns the
     // GPU; `busy=skip` keeps the last verdict, `busy=shrink` verifies a small prefix without re-keying
@@ -665,8 +734,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
                     if (q == cudaErrorNotReady) continue;
                     if (q != cudaSuccess) res[i]->ce = q;
                 }
-                cudaSetDevice(g->ordinal);
-                probe_collect(g, res[i].get());
+                probe_collect(g, res[i].get());  // no driver call unless event-timed or a repair is due
                 state[i] = 1;
                 --pending;
             }
@@ -705,12 +773,10 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             err = cuda_err("probe", r.ce) + " on " + be->gpus[i]->dev.id;
             continue;
         }
-        {
-            std::array<unsigned long long, 32> bcs;  // cached per size
-            if ((rc = get_bitcounts(be, r.n_vec * 4, bcs, err)) != B2DP_OK) { o.err = B2DP_E_CUDA; o.healthy = 0; continue; }
-            o.expected_checksum = expected_checksum(bcs, r.n_vec * 4, r.seed);
-            o.bytes = 2ull * r.n_vec * 16;
-        }
+        Gpu* g = be->gpus[i].get();
+        o.expected_checksum = expected_checksum_from_counts(
+            r.n_vec == g->n_vec ? g->bc : host_bitcounts(be, r.n_vec * 4), r.n_vec * 4, r.seed);  // host closed form
+        o.bytes = 2ull * r.n_vec * 16;
         o.checksum = r.out.checksum;
         o.mismatches = r.out.mismatches;
         o.first_bad_word = r.out.first_bad;
@@ -718,9 +784,28 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.ms_device = (float)((double)(r.out.t_end_ns - r.out.t_start_ns) * 1e-6);
         const float ms_for_rate = r.timed ? r.ms : o.ms_device;
         o.gbs = ms_for_rate > 0 ? (float)((double)o.bytes / (double)ms_for_rate * 1e-6) : 0.f;
-        // verdict (oracle/probe.py probe_healthy)
-        // a shrunk pass shares the GPU with a tenant: integrity only, no bandwidth floor
-        const bool fast_enough = (o.flags & (B2DP_RES_SHRUNK | B2DP_RES_SMALL_RING)) ? true : o.gbs >= min_gbs;
+        o.gbs_ref = g->gbs_ref.load();
+        o.frac = o.gbs_ref > 0 ? o.gbs / o.gbs_ref : 0.f;
+        // verdict (oracle/probe.py probe_healthy).  No GB/s floor for a pass that shares the GPU with a tenant by
+        // design (shrunk / small ring); the fractional floor needs a ring that streams from HBM (> the 126 MB L2).
+        float floor = 0.f;
+        if (!(o.flags & (B2DP_RES_SHRUNK | B2DP_RES_SMALL_RING))) {
+            if (abs_floor > 0) floor = abs_floor;
+            else if (o.bytes / 2 >= kFloorMinBytes && o.gbs_ref > 0) floor = be->cfg.min_frac * o.gbs_ref;
+            else o.flags |= B2DP_RES_NO_FLOOR;
+        }
+        o.min_gbs_applied = floor;
+        bool fast_enough = o.gbs >= floor;
+        if (!fast_enough) {
+            o.flags |= B2DP_RES_SLOW;
+            // Slow path only: a pass that shared HBM bandwidth with another process on the GPU says nothing about the
+            // part.  NVML counts the compute processes; this one holds one context itself.
+            unsigned cnt = 0;
+            if (be->nvml.ok && be->nvml.running_procs && g->nvh) {
+                const int nrc = be->nvml.running_procs(g->nvh, &cnt, nullptr);  // count only (INSUFFICIENT_SIZE = 7)
+                if ((nrc == 0 || nrc == 7) && cnt > 1) { o.flags |= B2DP_RES_CONTENDED; fast_enough = true; }
+            }
+        }
         o.healthy = (r.seq_ok && o.mismatches == 0 && o.checksum == o.expected_checksum && fast_enough) ? 1 : 0;
         if (be->cfg.check_ecc && be->gpus[i]->have_ecc) {  // opt-in: an NVML query per device per pass
             unsigned long long now = 0;
@@ -755,16 +840,20 @@ static Gpu* gpu_at(CudaBackend* be, int device, std::string& err) {
 }
 
 int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask, std::string& err) {
-    std::lock_guard<std::mutex> pl(be->probe_mu);
-    Gpu* g = gpu_at(be, device, err);
-    if (!g) return B2DP_E_INVAL;
     if (word == ~0ull) {  // synthetic critical-Xid event `mask`, handled like one delivered by NVML (xid=1)
+        Gpu* g = gpu_at(be, device, err);
+        if (!g) return B2DP_E_INVAL;
+        // like xid_listener: no backend lock is held while the context's callback runs (it takes the context lock,
+        // and Start()/labels/export take that lock before probe_mu)
         if (be->cfg.check_xid && !xid_is_application_error(mask)) {
             latch_xid(g, mask);
             be->fire_health_event();
         }
         return B2DP_OK;
     }
+    std::lock_guard<std::mutex> pl(be->probe_mu);
+    Gpu* g = gpu_at(be, device, err);
+    if (!g) return B2DP_E_INVAL;
     if (word >= g->n_vec * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
     cudaError_t ce = cudaSuccess;
     run_sync(g, [&] {
@@ -808,6 +897,27 @@ int cuda_probe_peek(CudaBackend* be, int device, uint64_t word, uint32_t* out, u
     return B2DP_OK;
 }
 
+// What the NVIDIA container runtime / a CDI spec calls the device `id` names: the GPU UUID (default, unambiguous)
+// or the NVML index.  NOT the /dev/nvidia minor: minors and NVML indices differ on HGX boards.
+std::string cuda_runtime_id(CudaBackend* be, const std::string& id, bool by_index) {
+    for (auto& g : be->gpus)
+        if (g->dev.id == id) {
+            if (by_index && g->nvml_index >= 0) return std::to_string(g->nvml_index);
+            return g->uuid;
+        }
+    return "";
+}
+
+int cuda_set_ref(CudaBackend* be, int device, float gbs_ref, std::string& err) {
+    if (device >= (int)be->gpus.size()) { err = "device index out of range"; return B2DP_E_INVAL; }
+    for (int i = 0; i < (int)be->gpus.size(); ++i) {
+        if (device >= 0 && device != i) continue;
+        Gpu* g = be->gpus[i].get();
+        g->gbs_ref.store(gbs_ref > 0 ? gbs_ref : g->gbs_cal);  // <= 0: back to this device's own calibration
+    }
+    return B2DP_OK;
+}
+
 // ---- P2P matrix ------------------------------------------------------------------------------
 constexpr float kNvlinkRefGbs = 770.f, kNvlinkClassFraction = 0.25f;  // oracle/probe.py
 
@@ -824,9 +934,7 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
     // a probe pass that missed its deadline still owns its GPU's seed/ring state: let the workers drain
     for (auto& g : be->gpus)
         if (g->inflight.load()) run_sync(g.get(), [] {});
-    std::array<unsigned long long, 32> bc;
-    int rc = get_bitcounts(be, n_vec * 4, bc, err);
-    if (rc != B2DP_OK) return rc;
+    const std::array<unsigned long long, 32>& bc = host_bitcounts(be, n_vec * 4);  // host closed form
 
     // peer capability + enable (on the reader's worker)
     std::vector<char> can((size_t)n * n, 0);
@@ -912,7 +1020,7 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
             const float g_ = (float)((double)bytes / (double)pr.best_ms * 1e-6);
             gbs[(size_t)i * n + j] = g_;
             uint64_t bad = pr.out.mismatches;
-            if (pr.out.checksum != expected_checksum(bc, n_vec * 4, be->gpus[j]->seed)) bad = bad ? bad : 1;
+            if (pr.out.checksum != expected_checksum_from_counts(bc, n_vec * 4, be->gpus[j]->seed)) bad = bad ? bad : 1;
             mism[(size_t)i * n + j] = bad;
         }
     }

@@ -75,6 +75,7 @@ struct LabelSource {  // what the generators read; filled by the backend
     // cuda backend answers (one entry per enumerated device, same order)
     bool native = false;
     std::vector<std::string> family, product_name, device_id, vbios;
+    std::vector<std::vector<std::pair<std::string, std::string>>> firmware;  // per device: (block, version) -- NVML
     std::vector<int64_t> vram_bytes, sm_count;
     std::string driver_version, driver_src_version;
     bool part_supported[2] = {false, false};
@@ -94,7 +95,10 @@ struct CudaConfig {
     uint64_t bytes = 1ull << 30;
     int slots = 2;                       // ring of probe buffers per GPU (2 = ping-pong; more = scrub window)
     uint64_t p2p_bytes = 256ull << 20;
-    float min_gbs = 3000.f;
+    float min_gbs = 0.f;                 // absolute GB/s floor (override); 0 = use min_frac of the calibrated ceiling
+    float min_frac = 0.8f;               // Healthy needs >= min_frac x gbs_ref (BASELINE.json: ">= 80 % of HBM peak")
+    float ref_gbs = 0.f;                 // the ceiling, if the operator pins it; 0 = calibrate at open
+    int calib = 3;                       // calibration passes per GPU at open (best kept)
     std::string sysroot = "/";
     int busy_policy = 0;                 // 0 probe always, 1 skip busy GPUs, 2 shrink on busy GPUs
     uint64_t shrink_bytes = 64ull << 20;
@@ -115,6 +119,8 @@ int cuda_p2p_matrix(CudaBackend*, const b2dp_p2p_opts* opts, float* gbs, int32_t
 int cuda_device_count(CudaBackend*);
 void cuda_label_source(CudaBackend*, LabelSource& src);
 float cuda_min_gbs(CudaBackend*);
+std::string cuda_runtime_id(CudaBackend*, const std::string& id, bool by_index);
+int cuda_set_ref(CudaBackend*, int device, float gbs_ref, std::string& err);
 // xid=1: called (from a backend thread, or from b2dp_probe_inject_fault) when a device-level Xid has been latched
 void cuda_set_health_event_callback(CudaBackend*, std::function<void()> fn);
 

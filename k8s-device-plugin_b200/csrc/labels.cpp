@@ -78,6 +78,13 @@ static std::string replace_product(std::string s) {  // main.go:211: " "->"_", "
     return o;
 }
 
+// a version string as part of a label key: Kubernetes allows [A-Za-z0-9_.-] there
+static std::string label_safe(const std::string& v) {
+    std::string o;
+    for (char ch : go::trim_space(v)) o.push_back(isalnum((unsigned char)ch) || ch == '.' || ch == '-' || ch == '_' ? ch : '_');
+    return o;
+}
+
 static bool enabled(const std::string& csv, const char* name) {
     size_t pos = 0;
     const size_t len = strlen(name);
@@ -106,16 +113,44 @@ int generate_labels(const std::vector<Device>& devs, const LabelSource& src, con
         if (!enabled(csv, g)) continue;
         const std::string name = g;
         std::map<std::string, int> counts;
-        if (name == "firmware") {  // main.go:116-144; libdrm on the reference side
-            if (src.native)
-                for (size_t i = 0; i < devs.size() && i < src.vbios.size(); ++i)
-                    if (!src.vbios[i].empty()) counts["vbios." + src.vbios[i]]++;
+        if (name == "firmware") {
+            // main.go:116-144: counts["<block>.feat.<n>"] / counts["<block>.fw.<n>"] per card, experimental prefix only.
+            // The reference asks libdrm (ioctl; no file form).  cuda backend: NVML's versioned blocks (VBIOS, InfoROM
+            // image / OEM / ECC / power objects, GSP firmware) as "<block>.fw.<version>"; kfd backend: the per-card
+            // side file b2dp_export_kfd_tree() writes ("<block> <version>" lines), absent on a real amdgpu sysfs.
+            for (size_t i = 0; i < devs.size(); ++i) {
+                if (src.native) {
+                    if (i >= src.firmware.size()) continue;
+                    for (const auto& bv : src.firmware[i]) counts[bv.first + ".fw." + label_safe(bv.second)]++;
+                } else {
+                    std::string data;
+                    if (!go::read_file(go::join(root, "sys/class/drm/card" + std::to_string(devs[i].card) + "/device/b2dp_firmware"), data))
+                        continue;
+                    size_t pos = 0;
+                    while (pos < data.size()) {
+                        size_t e = data.find('\n', pos);
+                        if (e == std::string::npos) e = data.size();
+                        const std::string line = data.substr(pos, e - pos);
+                        pos = e + 1;
+                        const size_t sp = line.find(' ');
+                        if (sp == std::string::npos || sp == 0 || sp + 1 >= line.size()) continue;
+                        counts[line.substr(0, sp) + ".fw." + label_safe(line.substr(sp + 1))]++;
+                    }
+                }
+            }
             const std::string pfx = label_prefix("firmware", true);
             for (auto& kv : counts) out[pfx + "." + kv.first] = std::to_string(kv.second);
-        } else if (name == "family") {  // main.go:145-158; libdrm on the reference side
-            if (src.native)
-                for (size_t i = 0; i < devs.size() && i < src.family.size(); ++i)
-                    if (!src.family[i].empty()) counts[src.family[i]]++;
+        } else if (name == "family") {  // main.go:145-158; libdrm on the reference side, same two sources as above
+            for (size_t i = 0; i < devs.size(); ++i) {
+                std::string fam;
+                if (src.native) { if (i < src.family.size()) fam = src.family[i]; }
+                else {
+                    std::string data;
+                    if (go::read_file(go::join(root, "sys/class/drm/card" + std::to_string(devs[i].card) + "/device/b2dp_family"), data))
+                        fam = go::trim_space(data);
+                }
+                if (!fam.empty()) counts[fam]++;
+            }
             create_labels("family", counts, out);
         } else if (name == "driver-version") {  // main.go:159-174
             out[label_prefix(name, false)] =

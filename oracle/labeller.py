@@ -108,10 +108,10 @@ def generate(name, gpus, sys_root="", drm=None):
             if d is None:
                 continue
             for fw, ver in d["feat"].items():
-                k = "%s.feat.%d" % (fw, ver)
+                k = "%s.feat.%s" % (fw, ver)          # %d in Go (uint32); %s here so an exported tree may carry NVML's dotted versions
                 counts[k] = counts.get(k, 0) + 1
             for fw, ver in d["fw"].items():
-                k = "%s.fw.%d" % (fw, ver)
+                k = "%s.fw.%s" % (fw, ver)
                 counts[k] = counts.get(k, 0) + 1
         pfx = createLabelPrefix("firmware", True)
         return {"%s.%s" % (pfx, k): str(v) for k, v in counts.items()}

@@ -16,5 +16,7 @@ int cuda_p2p_matrix(CudaBackend*, const b2dp_p2p_opts*, float*, int32_t*, uint64
 int cuda_device_count(CudaBackend*) { return 0; }
 void cuda_label_source(CudaBackend*, LabelSource&) {}
 float cuda_min_gbs(CudaBackend*) { return 0.f; }
+std::string cuda_runtime_id(CudaBackend*, const std::string&, bool) { return ""; }
+int cuda_set_ref(CudaBackend*, int, float, std::string&) { return B2DP_E_NOGPU; }
 void cuda_set_health_event_callback(CudaBackend*, std::function<void()>) {}
 }  // namespace b2dp

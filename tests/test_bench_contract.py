@@ -20,8 +20,13 @@ def test_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["n_gpus"] == 1
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the two arms print the SAME config object (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config(1)
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"] > 0
+    assert cb["cycle_ms_kfd_walk"] > 0 and "the full buffer" in cb["sample"]
     e = d["e2e"]
     assert (e["value"], e["unit"], e["h2d_bytes_per_step"], e["d2h_bytes_per_step"]) == (d["value"], d["unit"], 0, 0)
 
@@ -57,4 +62,19 @@ def test_product_never_imports_links_or_executes_the_oracle():
     for m in re.finditer(r"^\s*from oracle import (\w+)", src, re.M):
         head = src[:m.start()]
         func = re.findall(r"^def (\w+)\(", head, re.M)[-1]
-        assert func in ("cpu_probe_baseline", "kfd_walk_baseline", "run_reference"), func
+        # parity_block: the untimed product-vs-oracle checker leg that runs after every timed region
+        assert func in ("cpu_probe_baseline", "kfd_walk_baseline", "run_reference", "parity_block"), func
+
+
+def test_reference_arm_does_not_load_the_product():
+    """The CPU arm must not import the product package or map libb200dp.so (the driver records the .so files each arm
+    loads): run it under a tracer that lists the shared objects mapped at exit."""
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1']\n"
+            "try:\n    runpy.run_path(%r, run_name='__main__')\nexcept SystemExit:\n    pass\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "sys.stderr.write('PRODUCT_SO=%%d\\n' %% ('libb200dp' in maps))\n"
+            "sys.stderr.write('PRODUCT_PKG=%%d\\n' %% any(m.startswith('k8s-device-plugin_b200') for m in sys.modules))\n"
+            % os.path.join(ROOT, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert "PRODUCT_SO=0" in r.stderr and "PRODUCT_PKG=0" in r.stderr, r.stderr[-2000:]

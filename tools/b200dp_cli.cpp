@@ -27,6 +27,10 @@ static int die(b2dp_ctx* c, const char* what, int rc) {
     return 1;
 }
 static double median(std::vector<double> v) { std::sort(v.begin(), v.end()); return v.empty() ? 0 : v[v.size() / 2]; }
+static double pct(std::vector<double> v, double q) {
+    std::sort(v.begin(), v.end());
+    return v.empty() ? 0 : v[(size_t)(q * (double)(v.size() - 1) + 0.5)];
+}
 
 int main(int argc, char** argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s <backend-uri> <command> [args]\n", argv[0]); return 2; }
@@ -63,8 +67,8 @@ int main(int argc, char** argv) {
         b2dp_cycle_stats st{};
         if ((rc = b2dp_list_and_watch(ctx, "gpu", nullptr, buf.data(), buf.size(), &len, &st)) != B2DP_OK)
             return die(ctx, "b2dp_list_and_watch(initial)", rc);
-        std::vector<double> wall, kern;
-        double bytes = 0;
+        std::vector<double> wall, kern, kmax, host;
+        double bytes = 0, frac_min = 1e30;
         for (int i = -5; i < steps; ++i) {
             const double t0 = now_ms();
             if (cmd == "probe") {
@@ -77,12 +81,22 @@ int main(int argc, char** argv) {
                 if ((rc = b2dp_list_and_watch(ctx, "gpu", &co, buf.data(), buf.size(), &len, &st)) != B2DP_OK) return die(ctx, "b2dp_list_and_watch", rc);
                 if (i >= 0) { bytes = (double)st.probe_bytes; if (st.n_unhealthy) return die(ctx, "unhealthy device", 0); }
             }
-            if (i >= 0) wall.push_back(now_ms() - t0);
+            if (i >= 0) {
+                wall.push_back(now_ms() - t0);
+                if (cmd == "cycle") {  // tail attribution: the slowest GPU's in-kernel span vs everything the host adds
+                    kmax.push_back(st.probe_ms_device_max);
+                    host.push_back(wall.back() - st.probe_ms_device_max);
+                    if (st.probe_frac_min > 0 && st.probe_frac_min < frac_min) frac_min = st.probe_frac_min;
+                }
+            }
         }
         const double w = median(wall);
-        printf("{\"command\": \"%s\", \"n_devices\": %d, \"steps\": %d, \"wall_ms_median\": %.4f, \"wall_ms_max\": %.4f, "
-               "\"aggregate_gbs\": %.1f, \"kernel_ms_median\": %.4f, \"response_bytes\": %zu}\n",
-               cmd.c_str(), n, steps, w, *std::max_element(wall.begin(), wall.end()), bytes / w / 1e6, median(kern), len);
+        printf("{\"command\": \"%s\", \"n_devices\": %d, \"steps\": %d, \"wall_ms_median\": %.4f, \"wall_ms_p99\": %.4f, "
+               "\"wall_ms_max\": %.4f, \"aggregate_gbs\": %.1f, \"kernel_ms_median\": %.4f, \"response_bytes\": %zu, "
+               "\"slowest_kernel_ms_p50\": %.4f, \"slowest_kernel_ms_p99\": %.4f, \"host_overhead_ms_p50\": %.4f, "
+               "\"host_overhead_ms_p99\": %.4f, \"probe_frac_min\": %.4f}\n",
+               cmd.c_str(), n, steps, w, pct(wall, 0.99), *std::max_element(wall.begin(), wall.end()), bytes / w / 1e6,
+               median(kern), len, pct(kmax, 0.5), pct(kmax, 0.99), pct(host, 0.5), pct(host, 0.99), frac_min > 1e29 ? 0.0 : frac_min);
     } else if (cmd == "resources") {
         char names[16][64];
         int m = 0;
