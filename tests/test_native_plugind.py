@@ -3,6 +3,7 @@ csrc/host/h2grpc.hpp, no Python, no gRPC library) against grpcio playing the kub
 directions -- grpcio's client (Huffman-coded, dynamically indexed HPACK, PINGs, flow control) drives the
 native server; the native client registers with a grpcio Registration server -- and the same RPC
 answers as the reference logic (oracle) on the reference's CPX capture.  CPU only (kfd: backend)."""
+V_ABI = 3          # B2DP_ABI_VERSION
 import os
 import signal
 import subprocess
@@ -135,7 +136,7 @@ def test_native_daemon_flag_and_start_errors(daemon_env):
                        capture_output=True, text=True)
     assert r.returncode == 1 and "invalid resource naming strategy: bogus" in r.stderr
     r = subprocess.run([EXE, "-version"], capture_output=True, text=True)
-    assert r.returncode == 0 and "libb200dp ABI 2" in r.stdout
+    assert r.returncode == 0 and "libb200dp ABI %d" % V_ABI in r.stdout
     r = subprocess.run([EXE, "-no_such_flag=1"], capture_output=True, text=True)
     assert r.returncode == 2 and "flag provided but not defined: -no_such_flag" in r.stderr
     r = subprocess.run([EXE, "-backend=kfd:" + root + "/nope"], capture_output=True, text=True)
