@@ -217,7 +217,8 @@ typedef struct b2dp_probe_result {
     float gbs;                  /* bytes / ms_event when event-timed, else bytes / ms_device */
     uint32_t flags;             /* B2DP_RES_* */
     float gbs_ref;              /* this device's ceiling: calibrated at open / ref_gbs= / b2dp_probe_set_ref */
-    float frac;                 /* gbs / gbs_ref (0 if there is no ceiling) */
+    float frac;                 /* (bytes / ms_device) / gbs_ref: the verdict's rate over the ceiling, both on the in-kernel
+                                   clock (0 if there is no ceiling) */
     float min_gbs_applied;      /* the floor the verdict used: min_gbs, else min_frac x gbs_ref, else 0 (none) */
     uint32_t reserved;
 } b2dp_probe_result;

@@ -506,8 +506,11 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
                 if (r.ce == cudaSuccess) r.ce = cudaStreamSynchronize(g->stream);
                 probe_collect(g, &r);
                 TRY(r.ce);
-                if (k == 0 || r.ms <= 0) continue;  // first pass warms clocks, TLBs and the instruction cache
-                const float gbs = (float)(2.0 * (double)g->n_vec * 16.0 / (double)r.ms * 1e-6);
+                // the verdict's clock is the in-kernel span (first CTA start .. result published): it is there on every
+                // pass, event-timed or not
+                const double span_ms = (double)(r.out.t_end_ns - r.out.t_start_ns) * 1e-6;
+                if (k == 0 || span_ms <= 0) continue;  // first pass warms clocks, TLBs and the instruction cache
+                const float gbs = (float)(2.0 * (double)g->n_vec * 16.0 / span_ms * 1e-6);
                 if (gbs > g->gbs_cal) g->gbs_cal = gbs;
             }
 #undef TRY
@@ -784,8 +787,11 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.ms_device = (float)((double)(r.out.t_end_ns - r.out.t_start_ns) * 1e-6);
         const float ms_for_rate = r.timed ? r.ms : o.ms_device;
         o.gbs = ms_for_rate > 0 ? (float)((double)o.bytes / (double)ms_for_rate * 1e-6) : 0.f;
+        // the verdict's rate: bytes over the in-kernel span, the same clock the ceiling was calibrated with (o.gbs is
+        // the event-timed figure when B2DP_PROBE_EVENT_TIMING asks for the roofline's clock)
+        const float gbs_span = o.ms_device > 0 ? (float)((double)o.bytes / (double)o.ms_device * 1e-6) : 0.f;
         o.gbs_ref = g->gbs_ref.load();
-        o.frac = o.gbs_ref > 0 ? o.gbs / o.gbs_ref : 0.f;
+        o.frac = o.gbs_ref > 0 ? gbs_span / o.gbs_ref : 0.f;
         // verdict (oracle/probe.py probe_healthy).  No GB/s floor for a pass that shares the GPU with a tenant by
         // design (shrunk / small ring); the fractional floor needs a ring that streams from HBM (> the 126 MB L2).
         float floor = 0.f;
@@ -795,7 +801,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             else o.flags |= B2DP_RES_NO_FLOOR;
         }
         o.min_gbs_applied = floor;
-        bool fast_enough = o.gbs >= floor;
+        bool fast_enough = gbs_span >= floor;
         if (!fast_enough) {
             o.flags |= B2DP_RES_SLOW;
             // Slow path only: a pass that shared HBM bandwidth with another process on the GPU says nothing about the

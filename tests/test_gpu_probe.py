@@ -613,22 +613,22 @@ def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
     part that lost bandwidth) -- flips on its own measured GB/s; ListAndWatch carries the verdict."""
     nbytes = 1 << 30
     with _open(P, nbytes) as ctx:
-        rs = [ctx.probe_health(timed=False)[0] for _ in range(6)]
-        assert all(r.healthy and r.gbs_ref > 0 and r.frac > 0.9 for r in rs), rs
+        rs = [ctx.probe_health(timed=False)[0] for _ in range(24)]
+        assert all(r.healthy and r.gbs_ref > 0 and 0.95 < r.frac < 1.03 for r in rs), rs
         ref0 = rs[0].gbs_ref
-        gbs = sorted(r.gbs for r in rs)[len(rs) // 2]
-        for frac, want in ((0.81, True), (0.79, False), (0.805, True), (0.795, False)):
+        gbs = sorted(r.gbs for r in rs[4:])[10]                    # timed=False: gbs is on the verdict's in-kernel clock
+        for frac, want in ((0.81, True), (0.79, False), (0.81, True), (0.79, False)):
             ctx.probe_set_ref(0, gbs / frac)
             for _ in range(3):
                 (r,) = ctx.probe_health(timed=False)
-                assert r.healthy == want and abs(r.frac - frac) < 0.004, (frac, r)
+                assert r.healthy == want and abs(r.frac - frac) < 0.008, (frac, r)
                 assert r.mismatches == 0 and r.checksum == r.expected_checksum and r.err == 0
                 assert bool(r.flags & P._native.RES_SLOW) == (not want)
                 assert abs(r.min_gbs_applied - 0.8 * r.gbs_ref) < 1.0
         ctx.probe_set_ref(0, gbs / 0.79)
         wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT)
         assert [d.health for d in P.v1beta1.ListAndWatchResponse.FromString(wire).devices] == ["Unhealthy"]
-        assert 0.78 < st.probe_frac_min < 0.80 and st.probe_ms_device_max > 0
+        assert 0.775 < st.probe_frac_min < 0.80 and st.probe_ms_device_max > 0
         ctx.probe_set_ref(0, 0.0)                                   # back to the calibration
         (r,) = ctx.probe_health(timed=False)
         assert r.healthy and abs(r.gbs_ref - ref0) < 1.0
@@ -637,8 +637,7 @@ def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
         for grid in (296, 222, 148, 111, 74, 37, 18):
             (r,) = ctx.probe_health(timed=False, grid_ctas=grid)
             assert r.mismatches == 0 and r.checksum == r.expected_checksum
-            if abs(r.frac - 0.8) > 0.004:
-                assert r.healthy == (r.frac >= 0.8), (grid, r)
+            assert r.healthy == (r.frac >= 0.8), (grid, r)
             verdicts.append((grid, round(r.frac, 3), r.healthy))
         assert verdicts[0][2] and not verdicts[-1][2], verdicts     # full grid Healthy, 18 CTAs far below the floor
         # absolute override: min_gbs replaces the fractional floor for a call ...
