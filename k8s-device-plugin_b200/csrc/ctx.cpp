@@ -190,6 +190,9 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else if (p.first == "min_frac") cfg.min_frac = (float)atof(p.second.c_str());
             else if (p.first == "ref_gbs") cfg.ref_gbs = (float)atof(p.second.c_str());
             else if (p.first == "calib") cfg.calib = atoi(p.second.c_str());
+            else if (p.first == "launchers") cfg.launchers = atoi(p.second.c_str());
+            else if (p.first == "spin_us") cfg.spin_us = atoi(p.second.c_str());
+            else if (p.first == "pin") cfg.pin_caller = p.second != "0";
             else if (p.first == "sysroot") cfg.sysroot = p.second;
             else if (p.first == "busy") {
                 if (p.second == "probe") cfg.busy_policy = 0;
@@ -214,6 +217,8 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         if (cfg.slots < 2 || cfg.slots > 4096) return fail(B2DP_E_INVAL, "slots must be in [2, 4096]");
         if (!(cfg.min_frac >= 0.f && cfg.min_frac <= 1.f)) return fail(B2DP_E_INVAL, "min_frac must be in [0, 1]");
         if (cfg.calib < 0 || cfg.calib > 64) return fail(B2DP_E_INVAL, "calib must be in [0, 64]");
+        if (cfg.launchers < 1 || cfg.launchers > 2) return fail(B2DP_E_INVAL, "launchers must be 1 or 2");
+        if (cfg.spin_us < 0 || cfg.spin_us > 100000) return fail(B2DP_E_INVAL, "spin_us must be in [0, 100000]");
         std::string err;
         CudaBackend* be = nullptr;
         int rc = cuda_backend_open(cfg, &be, err);
@@ -552,6 +557,10 @@ static void watch_loop(b2dp_watch* w) {
             std::unique_lock<std::mutex> l(w->mu);
             auto pred = [&] { return w->stop || w->pending_beats > 0; };
             if (w->pulse_ms) {
+                // launchers=2: wake the helper launcher a moment before the tick so the fan-out finds it spinning
+                if (w->ctx->kind == b2dp_ctx::CUDA && w->pulse_ms >= 2 &&
+                    !w->cv.wait_until(l, next - std::chrono::microseconds(300), pred))
+                    cuda_prearm(w->ctx->cuda);
                 if (!w->cv.wait_until(l, next, pred)) {  // ticker fired
                     next += std::chrono::milliseconds(w->pulse_ms);
                     w->pending_beats++;

@@ -14,6 +14,8 @@
 // CUDA/NVML/sysfs queries; the record layout and id formats are the reference's.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <array>
@@ -172,6 +174,24 @@ struct Gpu {
     std::vector<char> peer_enabled;
 };
 
+// launchers=2: a second launcher thread enqueues the passes of the GPUs on the OTHER NUMA node while the caller
+// enqueues its own half, so the last GPU starts ~half as late.  The helper spins for `spin_us` after a fan-out (and after
+// cuda_prearm(), which the library's own ListAndWatch loop calls just before a tick is due) and sleeps on a condition
+// variable otherwise; woken from sleep it still does the right thing, only later.
+struct ProbeJobResult;
+struct Launcher {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<unsigned long long> cmd{0}, done{0};
+    std::atomic<bool> sleeping{false}, quit{false}, arm{false};
+    std::vector<size_t> idx;  // gpu indices this thread launches on
+    // the job (written by the caller before cmd is bumped, read by the helper after it sees the new cmd)
+    std::vector<std::shared_ptr<ProbeJobResult>>* res = nullptr;
+    std::vector<char>* state = nullptr;
+    uint32_t variant = 0;
+};
+
 class CudaBackend {
 public:
     CudaConfig cfg;
@@ -180,6 +200,10 @@ public:
     std::string driver_version, driver_src_version;
     std::mutex probe_mu;  // one fan-out at a time
     std::mutex bc_mu;
+    std::unique_ptr<Launcher> launcher;              // launchers=2
+    std::vector<size_t> caller_idx;                  // the GPUs the calling thread enqueues (all of them without a launcher)
+    cpu_set_t caller_cpus;                           // pin=1: CPUs local to the caller's GPUs
+    bool have_caller_cpus = false;
     void* xid_set = nullptr;                         // NVML event set (xid=1), waited on by xid_thread only
     std::thread xid_thread;
     std::atomic<bool> xid_quit{false};
@@ -315,6 +339,66 @@ static void probe_collect(Gpu* g, ProbeJobResult* r) {
         hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
         cudaStreamSynchronize(g->stream);
     }
+}
+
+// "0-31,64-95" -> cpu_set_t
+static bool parse_cpulist(const std::string& text, cpu_set_t* set) {
+    CPU_ZERO(set);
+    bool any = false;
+    size_t pos = 0;
+    while (pos < text.size()) {
+        size_t e = text.find(',', pos);
+        if (e == std::string::npos) e = text.size();
+        const std::string item = text.substr(pos, e - pos);
+        pos = e + 1;
+        if (item.empty()) continue;
+        const size_t dash = item.find('-');
+        const int lo = atoi(item.c_str()), hi = dash == std::string::npos ? lo : atoi(item.c_str() + dash + 1);
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) { if (c >= 0) { CPU_SET(c, set); any = true; } }
+    }
+    return any;
+}
+
+static void launcher_loop(CudaBackend* be, Launcher* L, int spin_us) {
+    unsigned long long seen = 0;
+    auto spin_until = std::chrono::steady_clock::now();
+    for (;;) {
+        // wait for the next command: spin inside the window, sleep outside it
+        for (;;) {
+            if (L->quit.load(std::memory_order_acquire)) return;
+            if (L->cmd.load(std::memory_order_acquire) != seen) break;
+            if (L->arm.exchange(false)) spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(4 * spin_us);
+            if (std::chrono::steady_clock::now() < spin_until) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+                continue;
+            }
+            std::unique_lock<std::mutex> l(L->mu);
+            L->sleeping.store(true);
+            L->cv.wait(l, [&] { return L->quit.load() || L->arm.load() || L->cmd.load() != seen; });
+            L->sleeping.store(false);
+        }
+        seen = L->cmd.load(std::memory_order_acquire);
+        for (size_t i : L->idx) {
+            Gpu* g = be->gpus[i].get();
+            if ((*L->state)[i] != 0) continue;
+            if (g->inflight.load()) { (*L->state)[i] = 2; continue; }
+            cudaSetDevice(g->ordinal);
+            probe_issue(g, (*L->res)[i].get(), L->variant);
+        }
+        L->done.store(seen, std::memory_order_release);
+        spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
+    }
+}
+
+// The library's ListAndWatch loop calls this shortly before a tick is due: the helper launcher leaves its condition
+// variable and spins, so the fan-out that follows finds it hot.
+void cuda_prearm(CudaBackend* be) {
+    Launcher* L = be->launcher.get();
+    if (!L) return;
+    L->arm.store(true);
+    if (L->sleeping.load()) { std::lock_guard<std::mutex> l(L->mu); L->cv.notify_one(); }
 }
 
 static void xid_listener(CudaBackend* be);
@@ -547,6 +631,29 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
                 if (!o->broken && o->name == g->name && o->n_vec == g->n_vec) ref = std::max(ref, o->gbs_cal);
         g->gbs_ref.store(ref);
     }
+    // launchers=2: split the GPUs by NUMA node (GPU 0's node stays with the caller; one NUMA node: split in halves)
+    for (size_t i = 0; i < be->gpus.size(); ++i) be->caller_idx.push_back(i);
+    if (cfg.launchers >= 2 && be->gpus.size() >= 2) {
+        auto L = std::make_unique<Launcher>();
+        be->caller_idx.clear();
+        const int numa0 = be->gpus[0]->dev.numa;
+        for (size_t i = 0; i < be->gpus.size(); ++i)
+            (be->gpus[i]->dev.numa == numa0 ? be->caller_idx : L->idx).push_back(i);
+        if (L->idx.empty()) {
+            be->caller_idx.clear();
+            for (size_t i = 0; i < be->gpus.size(); ++i) (i < (be->gpus.size() + 1) / 2 ? be->caller_idx : L->idx).push_back(i);
+        }
+        Launcher* raw = L.get();
+        CudaBackend* bp = be.get();
+        raw->th = std::thread(launcher_loop, bp, raw, cfg.spin_us);
+        cpu_set_t set;  // keep the helper on the CPUs next to its GPUs
+        if (parse_cpulist(read_trim(go::join(cfg.sysroot, "sys/bus/pci/devices/" + be->gpus[raw->idx[0]]->dev.id + "/local_cpulist")), &set))
+            pthread_setaffinity_np(raw->th.native_handle(), sizeof set, &set);
+        be->launcher = std::move(L);
+    }
+    if (cfg.pin_caller)
+        be->have_caller_cpus = parse_cpulist(
+            read_trim(go::join(cfg.sysroot, "sys/bus/pci/devices/" + be->gpus[be->caller_idx[0]]->dev.id + "/local_cpulist")), &be->caller_cpus);
     *out = be.release();
     return B2DP_OK;
 }
@@ -556,6 +663,11 @@ void cuda_backend_close(CudaBackend* be) {
     be->xid_quit = true;
     if (be->xid_thread.joinable()) be->xid_thread.join();
     { std::lock_guard<std::mutex> l(be->xid_cb_mu); be->on_health_event = nullptr; }
+    if (be->launcher) {
+        be->launcher->quit.store(true);
+        { std::lock_guard<std::mutex> l(be->launcher->mu); be->launcher->cv.notify_all(); }
+        if (be->launcher->th.joinable()) be->launcher->th.join();
+    }
     for (auto& gp : be->gpus) {
         Gpu* g = gp.get();
         if (!g->th.joinable()) continue;
@@ -715,12 +827,28 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         // current CUDA device is restored before returning.
         int prev_dev = -1;
         cudaGetDevice(&prev_dev);
-        for (size_t i = 0; i < n; ++i) {
+        if (be->have_caller_cpus) {  // pin=1: keep the enqueue + poll thread on the CPUs next to its GPUs (once per thread)
+            static thread_local const CudaBackend* pinned_for = nullptr;
+            if (pinned_for != be) { pthread_setaffinity_np(pthread_self(), sizeof be->caller_cpus, &be->caller_cpus); pinned_for = be; }
+        }
+        Launcher* L = be->launcher.get();
+        unsigned long long cmd = 0;
+        if (L) {  // hand the other NUMA node's GPUs to the helper, then enqueue our own
+            L->res = &res; L->state = &state; L->variant = variant;
+            cmd = L->cmd.fetch_add(1, std::memory_order_release) + 1;
+            if (L->sleeping.load()) { std::lock_guard<std::mutex> l(L->mu); L->cv.notify_one(); }
+        }
+        for (size_t i : be->caller_idx) {
             Gpu* g = be->gpus[i].get();
             if (state[i] != 0) continue;
             if (g->inflight.load()) { state[i] = 2; continue; }
             cudaSetDevice(g->ordinal);
             probe_issue(g, res[i].get(), variant);
+        }
+        if (L) while (L->done.load(std::memory_order_acquire) != cmd) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
         }
         size_t pending = 0;
         for (size_t i = 0; i < n; ++i) pending += state[i] == 0;

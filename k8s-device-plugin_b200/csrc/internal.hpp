@@ -99,6 +99,9 @@ struct CudaConfig {
     float min_frac = 0.8f;               // Healthy needs >= min_frac x gbs_ref (BASELINE.json: ">= 80 % of HBM peak")
     float ref_gbs = 0.f;                 // the ceiling, if the operator pins it; 0 = calibrate at open
     int calib = 3;                       // calibration passes per GPU at open (best kept)
+    int launchers = 1;                   // 2: a helper thread enqueues the other NUMA node's GPUs in parallel with the caller
+    int spin_us = 500;                   // how long the helper keeps spinning after a fan-out / a pre-arm before it sleeps
+    bool pin_caller = false;             // pin=1: the fan-out's calling thread is bound to the CPUs local to its GPUs
     std::string sysroot = "/";
     int busy_policy = 0;                 // 0 probe always, 1 skip busy GPUs, 2 shrink on busy GPUs
     uint64_t shrink_bytes = 64ull << 20;
@@ -121,6 +124,7 @@ void cuda_label_source(CudaBackend*, LabelSource& src);
 float cuda_min_gbs(CudaBackend*);
 std::string cuda_runtime_id(CudaBackend*, const std::string& id, bool by_index);
 int cuda_set_ref(CudaBackend*, int device, float gbs_ref, std::string& err);
+void cuda_prearm(CudaBackend*);
 // xid=1: called (from a backend thread, or from b2dp_probe_inject_fault) when a device-level Xid has been latched
 void cuda_set_health_event_callback(CudaBackend*, std::function<void()> fn);
 

@@ -18,5 +18,6 @@ void cuda_label_source(CudaBackend*, LabelSource&) {}
 float cuda_min_gbs(CudaBackend*) { return 0.f; }
 std::string cuda_runtime_id(CudaBackend*, const std::string&, bool) { return ""; }
 int cuda_set_ref(CudaBackend*, int, float, std::string&) { return B2DP_E_NOGPU; }
+void cuda_prearm(CudaBackend*) {}
 void cuda_set_health_event_callback(CudaBackend*, std::function<void()>) {}
 }  // namespace b2dp

@@ -668,3 +668,36 @@ def test_expected_checksum_is_the_host_closed_form(P):
             out = C.c_uint64(0)
             assert P._native.lib.b2dp_expected_checksum(nbytes // 4, r.seed, C.byref(out)) == 0
             assert r.expected_checksum == out.value == r.checksum == oprobe.expected_checksum(nbytes // 4, r.seed)
+
+
+def test_helper_launcher_path_equals_direct_path(P):
+    """`launchers=2,pin=1`: a second thread enqueues the other half of the GPUs while the caller enqueues its own.  Same
+    state machine, same answers: seeds, checksums and verdicts equal those of a default context pass by pass, a fault
+    on a helper-launched GPU is caught once, and the library's own ListAndWatch loop (which pre-arms the helper before
+    each tick) streams Healthy."""
+    import queue
+    import torch
+    n = torch.cuda.device_count()
+    nbytes = 64 * MiB + 16 * 9
+    with P.Context("cuda:bytes=%d,launchers=2,pin=1,spin_us=200" % nbytes) as a, P.Context("cuda:bytes=%d" % nbytes) as b:
+        for step in range(5):
+            ra, rb = a.probe_health(min_gbs=1e-3, timed=bool(step % 2)), b.probe_health(min_gbs=1e-3)
+            assert [(r.seed, r.checksum, r.expected_checksum, r.mismatches, r.healthy) for r in ra] == \
+                   [(r.seed, r.checksum, r.expected_checksum, r.mismatches, r.healthy) for r in rb]
+            assert all(r.healthy for r in ra) and len(ra) == n
+        a.probe_inject_fault(n - 1, 4321, 0x8)                   # the last GPU is the helper's when there are >= 2
+        ra = a.probe_health(min_gbs=1e-3)
+        assert [r.healthy for r in ra] == [True] * (n - 1) + [False] and ra[-1].first_bad_word == 4321
+        assert all(r.healthy for r in a.probe_health(min_gbs=1e-3))
+        got = queue.Queue()
+        w = a.watch(lambda rc, wire, st: got.put((rc, wire, st)), pulse_ms=10, min_gbs=1e-3)
+        try:
+            for _ in range(6):
+                rc, wire, st = got.get(timeout=10)
+                assert rc == 0 and st.n_unhealthy == 0 and st.n_devices == n
+        finally:
+            w.stop()
+    for bad in ("cuda:devices=0,launchers=3", "cuda:devices=0,spin_us=-1", "cuda:devices=0,min_frac=2", "cuda:devices=0,calib=99",
+                "cuda:devices=0,id_strategy=minor"):
+        with pytest.raises(P._native.B2dpError):
+            P.Context(bad)
