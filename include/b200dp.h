@@ -249,6 +249,21 @@ B2DP_API int b2dp_probe_reset(b2dp_ctx *ctx, int device);
 /* Set the bandwidth ceiling (gbs_ref) of `device` (-1 = all) the fractional floor refers to, e.g. to the site's measured
  * HBM peak; gbs_ref <= 0 restores the device's own calibration.  Also how tests move a device across the 0.8 line. */
 B2DP_API int b2dp_probe_set_ref(b2dp_ctx *ctx, int device, float gbs_ref);
+/* What the probe holds on `device` (enumeration index): ring geometry, the calibrated ceiling, and the identity the
+ * container runtime knows the device by.  No pass runs. */
+typedef struct b2dp_probe_info {
+    uint64_t slot_bytes;     /* bytes per ring slot on this device (bytes= unless HBM was short at open) */
+    uint64_t total_memory;   /* device (or MIG instance) memory in bytes */
+    int32_t sm_count;
+    int32_t slots;
+    float gbs_cal;           /* best calibration pass of this device */
+    float gbs_ref;           /* the ceiling in force (sibling maximum / ref_gbs= / b2dp_probe_set_ref) */
+    int32_t usable;          /* 0: the device could not be set up (listed, always Unhealthy) */
+    int32_t via_helper;      /* 1: probed by a b200dp_probe_helper child (probe=helpers, MIG) */
+    char uuid[48];           /* "GPU-..." / "MIG-..." */
+    char name[64];           /* product name */
+} b2dp_probe_info;
+B2DP_API int b2dp_probe_describe(b2dp_ctx *ctx, int device, b2dp_probe_info *out);
 /* Closed-form checksum of a clean probe buffer of n_words 32-bit words keyed with `seed`, computed on the host
  * (the value b2dp_probe_result.expected_checksum carries).  No context, no GPU. */
 B2DP_API int b2dp_expected_checksum(uint64_t n_words, uint32_t seed, uint64_t *checksum);

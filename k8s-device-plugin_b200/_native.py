@@ -97,6 +97,12 @@ class CycleStats(C.Structure):
                 ("n_link_faults", C.c_int32), ("probe_ms_device_max", C.c_float), ("probe_frac_min", C.c_float)]
 
 
+class ProbeInfo(C.Structure):
+    _fields_ = [("slot_bytes", C.c_uint64), ("total_memory", C.c_uint64), ("sm_count", C.c_int32), ("slots", C.c_int32),
+                ("gbs_cal", C.c_float), ("gbs_ref", C.c_float), ("usable", C.c_int32), ("via_helper", C.c_int32),
+                ("uuid", C.c_char * 48), ("name", C.c_char * 64)]
+
+
 class P2pOpts(C.Structure):
     _fields_ = [("bytes", C.c_uint64), ("iters", C.c_uint32), ("flags", C.c_uint32)]
 
@@ -138,6 +144,7 @@ SIGNATURES = {
     "b2dp_probe_reset": (_i, [_vp, _i]),
     "b2dp_probe_peek": (_i, [_vp, _i, C.c_uint64, _P(C.c_uint32), C.c_uint64]),
     "b2dp_probe_set_ref": (_i, [_vp, _i, C.c_float]),
+    "b2dp_probe_describe": (_i, [_vp, _i, _P(ProbeInfo)]),
     "b2dp_expected_checksum": (_i, [C.c_uint64, C.c_uint32, _P(C.c_uint64)]),
     "b2dp_merge_health": (_i, [_P(Id64), _i, C.c_int32, _i, _P(Id64), _i32p, _i, _i32p]),
     "b2dp_list_and_watch": (_i, [_vp, _cp, _P(CycleOpts), _u8p, C.c_size_t, _szp, _P(CycleStats)]),

@@ -190,6 +190,17 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else if (p.first == "min_frac") cfg.min_frac = (float)atof(p.second.c_str());
             else if (p.first == "ref_gbs") cfg.ref_gbs = (float)atof(p.second.c_str());
             else if (p.first == "calib") cfg.calib = atoi(p.second.c_str());
+            else if (p.first == "probe") {
+                if (p.second == "inproc") cfg.probe_mode = 0;
+                else if (p.second == "helpers") cfg.probe_mode = 1;
+                else if (p.second == "off") cfg.probe_mode = 2;
+                else return fail(B2DP_E_INVAL, "probe= wants inproc|helpers|off");
+            } else if (p.first == "mig") {
+                if (p.second == "auto") cfg.mig_auto = true;
+                else if (p.second == "off") cfg.mig_auto = false;
+                else return fail(B2DP_E_INVAL, "mig= wants auto|off");
+            } else if (p.first == "mig_bytes") cfg.mig_bytes = strtoull(p.second.c_str(), nullptr, 0);
+            else if (p.first == "seed_index") cfg.seed_index = atoi(p.second.c_str());
             else if (p.first == "launchers") cfg.launchers = atoi(p.second.c_str());
             else if (p.first == "spin_us") cfg.spin_us = atoi(p.second.c_str());
             else if (p.first == "pin") cfg.pin_caller = p.second != "0";
@@ -214,6 +225,12 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else return fail(B2DP_E_INVAL, "unknown cuda: option " + p.first);
         }
         if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");
+        if (cfg.mig_bytes < 4096 || cfg.mig_bytes % 16) return fail(B2DP_E_INVAL, "mig_bytes must be a multiple of 16, >= 4096");
+        // what every helper process inherits: the verdict-related options (the ring geometry is set per unit)
+        for (const char* k : {"min_gbs", "min_frac", "ref_gbs", "calib", "busy", "shrink_bytes", "ecc"}) {
+            auto it = kv.find(k);
+            if (it != kv.end()) cfg.passthrough += std::string(",") + k + "=" + it->second;
+        }
         if (cfg.slots < 2 || cfg.slots > 4096) return fail(B2DP_E_INVAL, "slots must be in [2, 4096]");
         if (!(cfg.min_frac >= 0.f && cfg.min_frac <= 1.f)) return fail(B2DP_E_INVAL, "min_frac must be in [0, 1]");
         if (cfg.calib < 0 || cfg.calib > 64) return fail(B2DP_E_INVAL, "calib must be in [0, 64]");
@@ -358,6 +375,14 @@ extern "C" int b2dp_probe_set_ref(b2dp_ctx* c, int device, float gbs_ref) {
     if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "cuda: backend only");
     std::string err;
     int rc = cuda_set_ref(c->cuda, device, gbs_ref, err);
+    return rc == B2DP_OK ? rc : fail(rc, err);
+}
+extern "C" int b2dp_probe_describe(b2dp_ctx* c, int device, b2dp_probe_info* out) {
+    if (!c || !out) return B2DP_E_INVAL;
+    if (c->kind != b2dp_ctx::CUDA) return fail(B2DP_E_UNSUPPORTED, "cuda: backend only");
+    std::string err;
+    memset(out, 0, sizeof *out);
+    int rc = cuda_describe(c->cuda, device, out, err);
     return rc == B2DP_OK ? rc : fail(rc, err);
 }
 extern "C" int b2dp_expected_checksum(uint64_t n_words, uint32_t seed, uint64_t* checksum) {
@@ -649,7 +674,15 @@ static int device_specs(b2dp_ctx* c, const char* const* ids, int n_ids, std::vec
             if (c->kind == b2dp_ctx::KFD) {  // plugin.go:375-386 (canonical order: card, renderD)
                 push("/dev/dri/card" + std::to_string(d.card));
                 push("/dev/dri/renderD" + std::to_string(d.render_d));
-            } else push("/dev/nvidia" + std::to_string(d.card));
+            } else {  // whole GPU: /dev/nvidia<minor>; MIG instance: the parent's node + its two capability nodes
+                std::vector<std::string> paths;
+                if (!cuda_device_paths(c->cuda, d.id, paths)) paths.push_back("/dev/nvidia" + std::to_string(d.card));
+                for (auto& pth : paths) {
+                    bool dup = false;  // instances of one GPU share the parent's node
+                    for (auto& have : specs) dup = dup || pth == have.host_path;
+                    if (!dup) push(pth);
+                }
+            }
             break;
         }
     }
@@ -1016,13 +1049,24 @@ extern "C" int b2dp_export_kfd_tree(b2dp_ctx* c, const char* dir_c) {
                      l.type, l.from, l.to, l.type == 11 ? 15 : 20);
             ok &= write_file(nd + "/io_links/" + std::to_string(li++) + "/properties", lp);
         }
-        // driver dir (amdgpu.go:155-217) + drm class files the label generators read
-        const std::string pci = dir + "/sys/module/amdgpu/drivers/pci:amdgpu/" + d.id;
-        ok &= write_file(pci + "/numa_node", std::to_string(d.numa) + "\n");
-        ok &= mkdirs(pci + "/drm/card" + std::to_string(d.card));
-        ok &= mkdirs(pci + "/drm/renderD" + std::to_string(d.render_d));
-        if (src.part_supported[0]) ok &= write_file(pci + "/available_compute_partition", "SPX\n");
-        if (src.part_supported[1]) ok &= write_file(pci + "/available_memory_partition", "NPS1\n");
+        // driver dir (amdgpu.go:155-217) + drm class files the label generators read.  A partition other than the
+        // first of its GPU is a platform device (amdgpu.go:221-265): no numa_node / partition files of its own, it
+        // inherits them from the PCI function with the same devID.
+        auto upper = [](std::string v) { for (auto& ch : v) ch = (char)toupper((unsigned char)ch); return v; };
+        if (d.id.compare(0, 11, "amdgpu_xcp_") == 0) {
+            const std::string plat = dir + "/sys/devices/platform/" + d.id;
+            ok &= mkdirs(plat + "/drm/card" + std::to_string(d.card));
+            ok &= mkdirs(plat + "/drm/renderD" + std::to_string(d.render_d));
+        } else {
+            const std::string pci = dir + "/sys/module/amdgpu/drivers/pci:amdgpu/" + d.id;
+            ok &= write_file(pci + "/numa_node", std::to_string(d.numa) + "\n");
+            ok &= mkdirs(pci + "/drm/card" + std::to_string(d.card));
+            ok &= mkdirs(pci + "/drm/renderD" + std::to_string(d.render_d));
+            if (!d.compute.empty()) ok &= write_file(pci + "/current_compute_partition", upper(d.compute) + "\n");
+            if (!d.memory.empty()) ok &= write_file(pci + "/current_memory_partition", upper(d.memory) + "\n");
+            if (src.part_supported[0]) ok &= write_file(pci + "/available_compute_partition", d.compute.empty() ? "SPX\n" : "SPX, " + upper(d.compute) + "\n");
+            if (src.part_supported[1]) ok &= write_file(pci + "/available_memory_partition", d.memory.empty() ? "NPS1\n" : upper(d.memory) + "\n");
+        }
         const std::string drm = dir + "/sys/class/drm/card" + std::to_string(d.card) + "/device";
         ok &= write_file(drm + "/device", devid_hex + "\n");
         ok &= write_file(drm + "/product_name", (i < src.product_name.size() ? src.product_name[i] : "") + "\n");

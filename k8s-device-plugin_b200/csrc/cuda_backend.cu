@@ -31,7 +31,9 @@
 #include "gosem.hpp"
 #include "hbm_probe.cuh"
 #include "internal.hpp"
+#include "nvml_dyn.hpp"
 #include "pattern_math.hpp"
+#include "units_backend.hpp"
 
 namespace b2dp {
 
@@ -63,62 +65,6 @@ __global__ void pattern_bit_counts(unsigned long long n_words, unsigned long lon
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[b], v);
     }
 }
-
-// ---- NVML (optional, resolved at run time) ---------------------------------------------------
-struct Nvml {
-    void* lib = nullptr;
-    int (*init)() = nullptr;
-    int (*driver_version)(char*, unsigned) = nullptr;
-    int (*handle_by_bus_id)(const char*, void**) = nullptr;
-    int (*minor_number)(void*, unsigned*) = nullptr;
-    int (*vbios)(void*, char*, unsigned) = nullptr;
-    int (*mig_mode)(void*, unsigned*, unsigned*) = nullptr;
-    int (*running_procs)(void*, unsigned*, void*) = nullptr;        // nvmlDeviceGetComputeRunningProcesses_v3
-    int (*ecc_total)(void*, int, int, unsigned long long*) = nullptr;  // nvmlDeviceGetTotalEccErrors
-    int (*remapped_rows)(void*, unsigned*, unsigned*, unsigned*, unsigned*) = nullptr;  // nvmlDeviceGetRemappedRows
-    struct EventData { void* device; unsigned long long type, data; unsigned gi, ci; };  // nvmlEventData_t
-    int (*event_set_create)(void**) = nullptr;
-    int (*register_events)(void*, unsigned long long, void*) = nullptr;
-    int (*event_wait)(void*, EventData*, unsigned) = nullptr;          // nvmlEventSetWait_v2
-    int (*event_set_free)(void*) = nullptr;
-    int (*shutdown)() = nullptr;
-    int (*index_of)(void*, unsigned*) = nullptr;                       // nvmlDeviceGetIndex
-    int (*uuid_of)(void*, char*, unsigned) = nullptr;                  // nvmlDeviceGetUUID
-    int (*inforom_image)(void*, char*, unsigned) = nullptr;            // nvmlDeviceGetInforomImageVersion
-    int (*inforom_object)(void*, int, char*, unsigned) = nullptr;      // nvmlDeviceGetInforomVersion(OEM 0 / ECC 1 / POWER 2)
-    int (*gsp_firmware)(void*, char*) = nullptr;                       // nvmlDeviceGetGspFirmwareVersion
-    bool ok = false;
-    ~Nvml() {
-        if (ok && shutdown) shutdown();  // nvmlInit/nvmlShutdown are reference counted
-        if (lib) dlclose(lib);
-    }
-    void load() {
-        // B2DP_NVML_LIBRARY: an alternative NVML (tests: tests/native/nvml_stub.cpp describes a MIG-partitioned node)
-        const char* alt = getenv("B2DP_NVML_LIBRARY");
-        lib = dlopen(alt && *alt ? alt : "libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
-        if (!lib) return;
-        init = (int (*)())dlsym(lib, "nvmlInit_v2");
-        shutdown = (int (*)())dlsym(lib, "nvmlShutdown");
-        driver_version = (int (*)(char*, unsigned))dlsym(lib, "nvmlSystemGetDriverVersion");
-        handle_by_bus_id = (int (*)(const char*, void**))dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2");
-        minor_number = (int (*)(void*, unsigned*))dlsym(lib, "nvmlDeviceGetMinorNumber");
-        vbios = (int (*)(void*, char*, unsigned))dlsym(lib, "nvmlDeviceGetVbiosVersion");
-        mig_mode = (int (*)(void*, unsigned*, unsigned*))dlsym(lib, "nvmlDeviceGetMigMode");
-        running_procs = (int (*)(void*, unsigned*, void*))dlsym(lib, "nvmlDeviceGetComputeRunningProcesses_v3");
-        ecc_total = (int (*)(void*, int, int, unsigned long long*))dlsym(lib, "nvmlDeviceGetTotalEccErrors");
-        remapped_rows = (int (*)(void*, unsigned*, unsigned*, unsigned*, unsigned*))dlsym(lib, "nvmlDeviceGetRemappedRows");
-        event_set_create = (int (*)(void**))dlsym(lib, "nvmlEventSetCreate");
-        register_events = (int (*)(void*, unsigned long long, void*))dlsym(lib, "nvmlDeviceRegisterEvents");
-        event_wait = (int (*)(void*, EventData*, unsigned))dlsym(lib, "nvmlEventSetWait_v2");
-        event_set_free = (int (*)(void*))dlsym(lib, "nvmlEventSetFree");
-        index_of = (int (*)(void*, unsigned*))dlsym(lib, "nvmlDeviceGetIndex");
-        uuid_of = (int (*)(void*, char*, unsigned))dlsym(lib, "nvmlDeviceGetUUID");
-        inforom_image = (int (*)(void*, char*, unsigned))dlsym(lib, "nvmlDeviceGetInforomImageVersion");
-        inforom_object = (int (*)(void*, int, char*, unsigned))dlsym(lib, "nvmlDeviceGetInforomVersion");
-        gsp_firmware = (int (*)(void*, char*))dlsym(lib, "nvmlDeviceGetGspFirmwareVersion");
-        ok = init && init() == 0;
-    }
-};
 
 struct Completion {
     std::mutex mu;
@@ -200,6 +146,7 @@ public:
     std::string driver_version, driver_src_version;
     std::mutex probe_mu;  // one fan-out at a time
     std::mutex bc_mu;
+    std::unique_ptr<UnitsBackend> units;             // probe=helpers / probe=off / MIG: the NVML-driven half (units_backend.hpp)
     std::unique_ptr<Launcher> launcher;              // launchers=2
     std::vector<size_t> caller_idx;                  // the GPUs the calling thread enqueues (all of them without a launcher)
     cpu_set_t caller_cpus;                           // pin=1: CPUs local to the caller's GPUs
@@ -404,15 +351,39 @@ void cuda_prearm(CudaBackend* be) {
 static void xid_listener(CudaBackend* be);
 
 int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err) {
+    auto be = std::make_unique<CudaBackend>();
+    be->cfg = cfg;
+    be->nvml.load();
+    // MIG: CUDA shows a process ONE compute instance (and then no other GPU), so a node with any MIG-enabled GPU is
+    // enumerated through NVML and probed by one helper process per unit; this process never creates a CUDA context.
+    int mode = cfg.probe_mode;
+    if (mode == 0 && cfg.mig_auto && be->nvml.ok && be->nvml.device_count && be->nvml.handle_by_index && be->nvml.mig_mode) {
+        unsigned cnt = 0;
+        if (be->nvml.device_count(&cnt) == 0)
+            for (unsigned i = 0; i < cnt; ++i) {
+                void* h = nullptr;
+                unsigned cur = 0, pend = 0;
+                if (be->nvml.handle_by_index(i, &h) == 0 && be->nvml.mig_mode(h, &cur, &pend) == 0 && cur == 1) mode = 1;
+            }
+    }
+    if (mode != 0) {
+        int rc = units_open(cfg, be->nvml, mode == 1, &be->units, err);
+        if (rc != B2DP_OK) return rc;
+        if (be->nvml.driver_version) {
+            char buf[96] = {0};
+            if (be->nvml.driver_version(buf, sizeof buf) == 0) be->driver_version = buf;
+        }
+        if (be->driver_version.empty()) be->driver_version = read_trim(go::join(cfg.sysroot, "sys/module/nvidia/version"));
+        be->driver_src_version = read_trim(go::join(cfg.sysroot, "sys/module/nvidia/srcversion"));
+        *out = be.release();
+        return B2DP_OK;
+    }
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0) {
         err = ce != cudaSuccess ? cuda_err("cudaGetDeviceCount", ce) : "no CUDA devices";
         return B2DP_E_NOGPU;
     }
-    auto be = std::make_unique<CudaBackend>();
-    be->cfg = cfg;
-    be->nvml.load();
     std::vector<int> ords = cfg.devices;
     if (ords.empty()) for (int i = 0; i < count; ++i) ords.push_back(i);
     for (int o : ords) if (o < 0 || o >= count) { err = "device ordinal out of range"; return B2DP_E_INVAL; }
@@ -527,9 +498,10 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         const unsigned long long bytes = cfg.bytes, n_vec = cfg.bytes / 16;
         const int idx = (int)i;
         const int calib = cfg.calib;
+        const int seed_idx = cfg.seed_index >= 0 ? cfg.seed_index + idx : idx;  // a helper's one device stands for unit seed_index
         g->buf.assign((size_t)cfg.slots, nullptr);
         (void)n_vec;
-        cs.push_back(post(g, [g, bytes, idx, calib, &errs, &where] {
+        cs.push_back(post(g, [g, bytes, idx, calib, seed_idx, &errs, &where] {
             cudaError_t e;
 #define TRY(x) if ((e = (x)) != cudaSuccess) { errs[idx] = e; where[idx] = #x; return; }
             TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
@@ -560,7 +532,7 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             TRY(cudaFuncSetAttribute(hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>,
                                      cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            g->seed = 0x5EED0000u | (uint32_t)(idx & 0xffff);
+            g->seed = 0x5EED0000u | (uint32_t)(seed_idx & 0xffff);
             g->cur = 0;
             hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[0], g->n_vec, g->seed);
             TRY(cudaGetLastError());
@@ -660,6 +632,7 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
 
 void cuda_backend_close(CudaBackend* be) {
     if (!be) return;
+    if (be->units) { units_close(be->units.get()); delete be; return; }
     be->xid_quit = true;
     if (be->xid_thread.joinable()) be->xid_thread.join();
     { std::lock_guard<std::mutex> l(be->xid_cb_mu); be->on_health_event = nullptr; }
@@ -688,7 +661,7 @@ void cuda_backend_close(CudaBackend* be) {
     delete be;
 }
 
-int cuda_device_count(CudaBackend* be) { return (int)be->gpus.size(); }
+int cuda_device_count(CudaBackend* be) { return be->units ? (int)be->units->units.size() : (int)be->gpus.size(); }
 float cuda_min_gbs(CudaBackend* be) { return be->cfg.min_gbs; }
 void cuda_set_health_event_callback(CudaBackend* be, std::function<void()> fn) {
     std::lock_guard<std::mutex> l(be->xid_cb_mu);
@@ -697,6 +670,7 @@ void cuda_set_health_event_callback(CudaBackend* be, std::function<void()> fn) {
 
 int cuda_enumerate(CudaBackend* be, std::vector<Device>& out, std::string&) {
     out.clear();
+    if (be->units) { for (auto& u : be->units->units) out.push_back(u.dev); return B2DP_OK; }
     for (auto& g : be->gpus) out.push_back(g->dev);
     return B2DP_OK;
 }
@@ -704,6 +678,10 @@ int cuda_enumerate(CudaBackend* be, std::vector<Device>& out, std::string&) {
 int cuda_node_health(CudaBackend* be) {
     // the analogue of "a GPU node exists in the kfd topology" (plugin.go:198-201):
     // the driver still answers and reports the devices this context was opened on
+    if (be->units) {  // no CUDA in this process: NVML must still count the physical GPUs the units live on
+        unsigned cnt = 0;
+        return be->nvml.device_count && be->nvml.device_count(&cnt) == 0 && cnt > 0 && !be->units->units.empty() ? 1 : 0;
+    }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
     return count >= (int)be->gpus.size() && !be->gpus.empty() ? 1 : 0;
@@ -713,6 +691,21 @@ void cuda_label_source(CudaBackend* be, LabelSource& src) {
     src.native = true;
     src.driver_version = be->driver_version;
     src.driver_src_version = be->driver_src_version;
+    if (be->units) {
+        bool migc = !be->units->units.empty();
+        for (auto& u : be->units->units) {
+            src.family.push_back(u.family);
+            src.product_name.push_back(u.name);
+            src.device_id.push_back(u.pci_device_id);
+            src.vbios.push_back(u.vbios);
+            src.firmware.push_back(u.firmware);
+            src.vram_bytes.push_back(u.vram);
+            src.sm_count.push_back(u.sms);
+            migc = migc && u.mig_capable;
+        }
+        src.part_supported[0] = src.part_supported[1] = migc;
+        return;
+    }
     bool mig = !be->gpus.empty();
     for (auto& g : be->gpus) {
         src.family.push_back(g->family);
@@ -766,6 +759,10 @@ static void xid_listener(CudaBackend* be) {
 
 int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_probe_result>& out, std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
+    if (be->units) {
+        if (!be->units->helpers) { err = "probe=off: this context enumerates only"; return B2DP_E_UNSUPPORTED; }
+        return units_probe(be->units.get(), opts, out, err);
+    }
     int rc = B2DP_OK;
     const uint32_t variant = opts ? (opts->flags & B2DP_PROBE_VARIANT_MASK) : 0;
     const bool via_workers = opts && (opts->flags & B2DP_PROBE_VIA_WORKERS);
@@ -973,7 +970,33 @@ static Gpu* gpu_at(CudaBackend* be, int device, std::string& err) {
     return be->gpus[device].get();
 }
 
+// helpers mode: forward a single-unit operation to the unit's child
+static int units_forward(CudaBackend* be, int device, HelperReq q, std::string& err, std::vector<uint32_t>* payload = nullptr) {
+    UnitsBackend* ub = be->units.get();
+    if (!ub->helpers) { err = "probe=off: this context enumerates only"; return B2DP_E_UNSUPPORTED; }
+    if (device < 0 || device >= (int)ub->units.size()) { err = "device index out of range"; return B2DP_E_INVAL; }
+    Unit& u = ub->units[device];
+    if (u.broken) { err = "device was not set up: " + u.broken_reason; return B2DP_E_INVAL; }
+    HelperRsp r{};
+    int rc = units_call(u, q, &r, 30000, payload);
+    if (rc == B2DP_OK && r.rc != B2DP_OK) { rc = r.rc; err = r.text; }
+    else if (rc != B2DP_OK) {
+        // the stream is out of step (a late answer may carry a payload): drop this child, the next heartbeat restarts it
+        err = "probe helper did not answer";
+        units_kill(u);
+        u.broken = true;
+        u.broken_reason = "probe helper unresponsive";
+    }
+    return rc;
+}
+
 int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask, std::string& err) {
+    if (be->units) {
+        std::lock_guard<std::mutex> pl(be->probe_mu);
+        HelperReq q{};
+        q.op = HOP_INJECT; q.a = word; q.b = mask;
+        return units_forward(be, device, q, err);
+    }
     if (word == ~0ull) {  // synthetic critical-Xid event `mask`, handled like one delivered by NVML (xid=1)
         Gpu* g = gpu_at(be, device, err);
         if (!g) return B2DP_E_INVAL;
@@ -1000,6 +1023,16 @@ int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask,
 
 int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
+    if (be->units) {
+        for (int i = 0; i < (int)be->units->units.size(); ++i) {
+            if ((device >= 0 && device != i) || be->units->units[i].broken) continue;
+            HelperReq q{};
+            q.op = HOP_RESET;
+            int rc = units_forward(be, i, q, err);
+            if (rc != B2DP_OK) return rc;
+        }
+        return device >= (int)be->units->units.size() ? B2DP_E_INVAL : B2DP_OK;
+    }
     for (int i = 0; i < (int)be->gpus.size(); ++i) {
         if (device >= 0 && device != i) continue;
         Gpu* g = be->gpus[i].get();
@@ -1018,6 +1051,19 @@ int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
 
 int cuda_probe_peek(CudaBackend* be, int device, uint64_t word, uint32_t* out, uint64_t n, std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
+    if (be->units) {
+        for (uint64_t done = 0; done < n;) {  // 1 Mi words per exchange
+            const uint64_t chunk = std::min<uint64_t>(n - done, 1u << 20);
+            HelperReq q{};
+            q.op = HOP_PEEK; q.a = word + done; q.b = chunk;
+            std::vector<uint32_t> payload;
+            int rc = units_forward(be, device, q, err, &payload);
+            if (rc != B2DP_OK) return rc;
+            memcpy(out + done, payload.data(), (size_t)chunk * 4);
+            done += chunk;
+        }
+        return B2DP_OK;
+    }
     Gpu* g = gpu_at(be, device, err);
     if (!g) return B2DP_E_INVAL;
     if (word + n > g->n_vec * 4) { err = "range out of bounds"; return B2DP_E_INVAL; }
@@ -1034,6 +1080,15 @@ int cuda_probe_peek(CudaBackend* be, int device, uint64_t word, uint32_t* out, u
 // What the NVIDIA container runtime / a CDI spec calls the device `id` names: the GPU UUID (default, unambiguous)
 // or the NVML index.  NOT the /dev/nvidia minor: minors and NVML indices differ on HGX boards.
 std::string cuda_runtime_id(CudaBackend* be, const std::string& id, bool by_index) {
+    if (be->units) {
+        for (auto& u : be->units->units)
+            if (u.dev.id == id) {
+                if (!by_index || u.nvml_index < 0) return u.uuid;
+                // NVIDIA_VISIBLE_DEVICES index syntax: "<gpu>" or "<gpu>:<mig device index>"
+                return u.mig_slot >= 0 ? std::to_string(u.nvml_index) + ":" + std::to_string(u.mig_slot) : std::to_string(u.nvml_index);
+            }
+        return "";
+    }
     for (auto& g : be->gpus)
         if (g->dev.id == id) {
             if (by_index && g->nvml_index >= 0) return std::to_string(g->nvml_index);
@@ -1043,6 +1098,21 @@ std::string cuda_runtime_id(CudaBackend* be, const std::string& id, bool by_inde
 }
 
 int cuda_set_ref(CudaBackend* be, int device, float gbs_ref, std::string& err) {
+    if (be->units) {
+        std::lock_guard<std::mutex> pl(be->probe_mu);
+        if (device >= (int)be->units->units.size()) { err = "device index out of range"; return B2DP_E_INVAL; }
+        for (int i = 0; i < (int)be->units->units.size(); ++i) {
+            if ((device >= 0 && device != i) || be->units->units[i].broken) continue;
+            Unit& u = be->units->units[i];
+            u.gbs_ref = gbs_ref > 0 ? gbs_ref : u.gbs_cal;
+            HelperReq q{};
+            q.op = HOP_SETREF;
+            memcpy(&q.a, &u.gbs_ref, sizeof(float));
+            int rc = units_forward(be, i, q, err);
+            if (rc != B2DP_OK) return rc;
+        }
+        return B2DP_OK;
+    }
     if (device >= (int)be->gpus.size()) { err = "device index out of range"; return B2DP_E_INVAL; }
     for (int i = 0; i < (int)be->gpus.size(); ++i) {
         if (device >= 0 && device != i) continue;
@@ -1052,12 +1122,58 @@ int cuda_set_ref(CudaBackend* be, int device, float gbs_ref, std::string& err) {
     return B2DP_OK;
 }
 
+int cuda_describe(CudaBackend* be, int device, b2dp_probe_info* o, std::string& err) {
+    if (device < 0 || device >= cuda_device_count(be)) { err = "device index out of range"; return B2DP_E_INVAL; }
+    if (be->units) {
+        const Unit& u = be->units->units[device];
+        o->slot_bytes = u.slot_bytes; o->total_memory = (uint64_t)u.vram; o->sm_count = (int32_t)u.sms; o->slots = be->cfg.slots;
+        o->gbs_cal = u.gbs_cal; o->gbs_ref = u.gbs_ref; o->usable = u.broken ? 0 : 1; o->via_helper = be->units->helpers ? 1 : 0;
+        copy_str(o->uuid, sizeof o->uuid, u.uuid);
+        copy_str(o->name, sizeof o->name, u.name);
+        return B2DP_OK;
+    }
+    const Gpu* g = be->gpus[device].get();
+    o->slot_bytes = g->n_vec * 16; o->total_memory = (uint64_t)g->vram; o->sm_count = (int32_t)g->sms; o->slots = (int32_t)g->buf.size();
+    o->gbs_cal = g->gbs_cal; o->gbs_ref = g->gbs_ref.load(); o->usable = g->broken ? 0 : 1; o->via_helper = 0;
+    copy_str(o->uuid, sizeof o->uuid, g->uuid);
+    copy_str(o->name, sizeof o->name, g->name);
+    return B2DP_OK;
+}
+
+bool cuda_device_paths(CudaBackend* be, const std::string& id, std::vector<std::string>& out) {
+    if (be->units) {
+        for (auto& u : be->units->units)
+            if (u.dev.id == id) {
+                out.push_back("/dev/nvidia" + std::to_string(u.parent_minor));
+                if (u.mig_slot >= 0) {  // a MIG instance needs its GPU-instance and compute-instance capability nodes too
+                    if (u.cap_gi >= 0) out.push_back("/dev/nvidia-caps/nvidia-cap" + std::to_string(u.cap_gi));
+                    if (u.cap_ci >= 0) out.push_back("/dev/nvidia-caps/nvidia-cap" + std::to_string(u.cap_ci));
+                }
+                return true;
+            }
+        return false;
+    }
+    for (auto& g : be->gpus)
+        if (g->dev.id == id) { out.push_back("/dev/nvidia" + std::to_string(g->dev.card)); return true; }
+    return false;
+}
+
 // ---- P2P matrix ------------------------------------------------------------------------------
 constexpr float kNvlinkRefGbs = 770.f, kNvlinkClassFraction = 0.25f;  // oracle/probe.py
 
 int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int32_t* link_type, uint64_t* mism, int n,
                     std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
+    if (be->units) {
+        // no CUDA context here and no P2P between MIG instances: the link classes are DECLARED from NVML (gbs = 0)
+        if (n != (int)be->units->units.size()) { err = "n must equal the device count"; return B2DP_E_INVAL; }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                gbs[(size_t)i * n + j] = 0; mism[(size_t)i * n + j] = 0;
+                link_type[(size_t)i * n + j] = i == j ? 0 : units_link_type(be->nvml, be->units->units[i], be->units->units[j]);
+            }
+        return B2DP_OK;
+    }
     if (n != (int)be->gpus.size()) { err = "n must equal the device count"; return B2DP_E_INVAL; }
     unsigned long long bytes = opts && opts->bytes ? opts->bytes : be->cfg.p2p_bytes;
     for (auto& g : be->gpus) if (!g->broken) bytes = std::min<unsigned long long>(bytes, g->n_vec * 16);  // the smallest ring slot bounds a pass

@@ -102,6 +102,11 @@ struct CudaConfig {
     int launchers = 1;                   // 2: a helper thread enqueues the other NUMA node's GPUs in parallel with the caller
     int spin_us = 500;                   // how long the helper keeps spinning after a fan-out / a pre-arm before it sleeps
     bool pin_caller = false;             // pin=1: the fan-out's calling thread is bound to the CPUs local to its GPUs
+    int probe_mode = 0;                  // 0 in-process (default), 1 helpers (one child process per unit), 2 off (NVML only)
+    bool mig_auto = true;                // mig=auto: a MIG-enabled GPU is listed as its MIG devices (forces helpers for the node)
+    uint64_t mig_bytes = 256ull << 20;   // ring slot size on a MIG instance
+    int seed_index = -1;                 // helpers: the enumeration index this one-device context stands for (seed schedule)
+    std::string passthrough;             // helpers: the probe-related URI options handed on to every child
     std::string sysroot = "/";
     int busy_policy = 0;                 // 0 probe always, 1 skip busy GPUs, 2 shrink on busy GPUs
     uint64_t shrink_bytes = 64ull << 20;
@@ -125,6 +130,10 @@ float cuda_min_gbs(CudaBackend*);
 std::string cuda_runtime_id(CudaBackend*, const std::string& id, bool by_index);
 int cuda_set_ref(CudaBackend*, int device, float gbs_ref, std::string& err);
 void cuda_prearm(CudaBackend*);
+int cuda_describe(CudaBackend*, int device, b2dp_probe_info* out, std::string& err);
+// device nodes Allocate mounts for `id` beyond the three global ones (whole GPU: /dev/nvidia<minor>; MIG instance:
+// the parent's node plus its two /dev/nvidia-caps nodes); false if the id is unknown
+bool cuda_device_paths(CudaBackend*, const std::string& id, std::vector<std::string>& out);
 // xid=1: called (from a backend thread, or from b2dp_probe_inject_fault) when a device-level Xid has been latched
 void cuda_set_health_event_callback(CudaBackend*, std::function<void()> fn);
 

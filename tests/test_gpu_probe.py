@@ -701,3 +701,84 @@ def test_helper_launcher_path_equals_direct_path(P):
                 "cuda:devices=0,id_strategy=minor"):
         with pytest.raises(P._native.B2dpError):
             P.Context(bad)
+
+
+def test_probe_through_helper_processes(P):
+    """probe=helpers: the parent never creates a CUDA context; one b200dp_probe_helper child per GPU (started with
+    CUDA_VISIBLE_DEVICES=<its UUID>) runs the ordinary probe.  This is the path every MIG instance takes (CUDA shows a
+    process a single compute instance); here it runs on whole GPUs so that it is verified on real hardware: passes are
+    bit-exact with the oracle, the seed schedule is the enumeration index's, faults are caught once, the fractional
+    floor applies, a killed helper is reported Unhealthy and restarted by the next heartbeat."""
+    import signal
+    import time
+    import torch
+    n = torch.cuda.device_count()
+    nbytes = 192 * MiB + 16 * 11
+    n_words = nbytes // 4
+    with P.Context("cuda:probe=helpers,bytes=%d" % nbytes) as ctx, P.Context("cuda:bytes=%d,calib=0" % MiB) as direct:
+        assert ctx.enumerate() == direct.enumerate()                 # same table as the in-process backend
+        info = P._native.ProbeInfo()
+        for i in range(n):
+            assert P._native.lib.b2dp_probe_describe(ctx._h, i, info) == 0
+            assert info.via_helper == 1 and info.usable == 1 and info.slot_bytes == nbytes and info.sm_count == 148
+            assert info.uuid.decode().startswith("GPU-") and info.gbs_ref >= info.gbs_cal > 1000.0
+        seeds = [oprobe.initial_seed(i) for i in range(n)]
+        for step in range(3):
+            before = ctx.probe_peek(n - 1, 0, n_words)
+            assert np.array_equal(before, oprobe.pattern(n_words, seeds[n - 1]))
+            res = ctx.probe_health(timed=False)
+            assert [r.device for r in res] == list(range(n)) and [r.seed for r in res] == seeds
+            for r in res:
+                assert r.err == 0 and r.healthy and r.mismatches == 0 and r.bytes == 2 * nbytes
+                assert r.checksum == r.expected_checksum == oprobe.expected_checksum(n_words, r.seed)
+                assert r.frac > 0.8 and abs(r.min_gbs_applied - 0.8 * r.gbs_ref) < 1.0
+            cs, bad, first, dst = oprobe.probe_pass(before, seeds[n - 1], oprobe.next_seed(seeds[n - 1]))
+            assert np.array_equal(ctx.probe_peek(n - 1, 0, n_words), dst)
+            seeds = [oprobe.next_seed(s) for s in seeds]
+        ctx.probe_inject_fault(0, 31337, 0x40)
+        res = ctx.probe_health(timed=False)
+        assert (res[0].healthy, res[0].mismatches, res[0].first_bad_word) == (False, 1, 31337)
+        assert all(r.healthy for r in res[1:])
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT)
+        assert st.n_devices == n and st.n_unhealthy == 0            # reported once; the helper re-filled its ring
+        ctx.probe_set_ref(0, 1e6)                                    # a ceiling no part reaches: below the 0.8 line
+        res = ctx.probe_health(timed=False)
+        assert not res[0].healthy and res[0].flags & P._native.RES_SLOW and all(r.healthy for r in res[1:])
+        ctx.probe_set_ref(0, 0.0)
+        assert all(r.healthy for r in ctx.probe_health(timed=False))
+        # Start(): no CUDA here, so the link classes are declared from NVML (NVLink on an HGX board), not measured
+        if n > 1:
+            assert ctx.start() == 0
+            ids = sorted(ctx.enumerate())
+            assert len(ctx.preferred_allocation(ids, [], 2)) == 2
+            gbs, lt, mm = ctx.p2p_matrix()
+            assert (gbs == 0).all() and all(lt[i, j] == 11 for i in range(n) for j in range(n) if i != j)
+        # kill one helper: Unhealthy with E_CUDA on the next pass, restarted by the one after
+        out = subprocess_pids_of_helpers()
+        assert len(out) >= n
+        os.kill(out[-1], signal.SIGKILL)
+        time.sleep(0.2)
+        res = ctx.probe_health(timed=False, min_gbs=1e-3)
+        dead = [r for r in res if r.err != 0]
+        assert len(dead) == 1 and dead[0].err == P._native.E_CUDA and not dead[0].healthy
+        res = ctx.probe_health(timed=False, min_gbs=1e-3)
+        assert all(r.err == 0 and r.healthy for r in res)
+    time.sleep(0.3)
+    assert subprocess_pids_of_helpers() == []                       # closing the context reaps every child
+
+
+def subprocess_pids_of_helpers():
+    """pids of this process's b200dp_probe_helper children (by /proc, no pattern kill)."""
+    me = os.getpid()
+    pids = []
+    for d in os.listdir("/proc"):
+        if not d.isdigit():
+            continue
+        try:
+            stat = open("/proc/%s/stat" % d).read()
+            ppid = int(stat.rsplit(")", 1)[1].split()[1])
+            if ppid == me and "b200dp_probe_h" in stat:
+                pids.append(int(d))
+        except OSError:
+            pass
+    return sorted(pids)
