@@ -296,10 +296,13 @@ static void on_send(void* user, int rc, const uint8_t* buf, size_t len, const b2
 }
 
 static int cmd_threads(char** argv) {
-    const std::string sysroot = argv[2];
+    // argv[2]: a sysroot (opened as kfd:<sysroot>) or a full backend uri ("cuda:probe=off,...": the NVML-driven units
+    // backend against whatever NVML B2DP_NVML_LIBRARY names)
+    const std::string arg = argv[2];
+    const std::string uri = arg.compare(0, 5, "cuda:") == 0 || arg.compare(0, 10, "synthetic:") == 0 ? arg : "kfd:" + arg;
     const int T = atoi(argv[3]), iters = atoi(argv[4]);
     b2dp_ctx* c = nullptr;
-    if (b2dp_open(("kfd:" + sysroot).c_str(), &c) != B2DP_OK) { fprintf(stderr, "open failed\n"); return 2; }
+    if (b2dp_open(uri.c_str(), &c) != B2DP_OK) { fprintf(stderr, "open failed: %s\n", b2dp_last_error(nullptr)); return 2; }
     (void)b2dp_start(c);
     const uint64_t want = ctx_pass(c, true);
     WatchCount wc;
@@ -316,7 +319,7 @@ static int cmd_threads(char** argv) {
                 if (w && i % 2 == 0) (void)b2dp_watch_beat(w);
                 if (i % 4 == t % 4) {                               // private contexts come and go meanwhile
                     b2dp_ctx* p = nullptr;
-                    if (b2dp_open(("kfd:" + sysroot).c_str(), &p) == B2DP_OK) { if (ctx_pass(p, true) != want) bad++; b2dp_close(p); }
+                    if (b2dp_open(uri.c_str(), &p) == B2DP_OK) { if (ctx_pass(p, true) != want) bad++; b2dp_close(p); }
                 }
             }
         });

@@ -30,7 +30,8 @@ SOURCES = [os.path.join(CSRC, f) for f in ("kfd.cpp", "allocator.cpp", "labels.c
 
 CACHE = os.path.join(HERE, "native", "_build")          # git-ignored; binaries are re-used while no source is newer
 HEADERS = [os.path.join(ROOT, "include", "b200dp.h")] + [os.path.join(CSRC, f) for f in
-           ("gosem.hpp", "internal.hpp", "pbwire.hpp", "hpack_huffman.inc", "host/h2grpc.hpp", "host/pbread.hpp")]
+           ("gosem.hpp", "internal.hpp", "pbwire.hpp", "hpack_huffman.inc", "host/h2grpc.hpp", "host/pbread.hpp",
+            "units_backend.hpp", "nvml_dyn.hpp", "helper_proto.hpp", "pattern_math.hpp")]
 
 
 def _fresh(out, sources):
@@ -113,6 +114,31 @@ def test_tsan_shared_context_many_threads(bins, trees, which):
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-6000:])
     assert "threads ok" in r.stdout and " 0 mismatching passes, 0 failures" in r.stdout
     assert "ThreadSanitizer" not in r.stderr
+
+
+@pytest.mark.parametrize("which", ["asan", "tsan"])
+def test_mig_enumeration_under_sanitizers(bins, which, tmp_path):
+    """The NVML-driven units backend (csrc/units_backend.hpp: MIG devices in the reference's CPX shape, declared links,
+    Allocate specs with /dev/nvidia-caps nodes, labels) on an 8 x 7-instance node described by tests/native/nvml_stub.cpp:
+    several threads on one shared `cuda:probe=off` context plus private contexts opening and closing, every pass equal
+    to the single-threaded digest."""
+    import test_mig_enumeration as tm
+    stub = tm.STUB
+    os.makedirs(tm.BUILD, exist_ok=True)
+    src = os.path.join(HERE, "native", "nvml_stub.cpp")
+    if not os.path.exists(stub) or os.path.getmtime(src) > os.path.getmtime(stub):
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fvisibility=hidden", src, "-o", stub],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    env = _env()
+    env["B2DP_NVML_LIBRARY"] = stub
+    env["B2DP_NVML_STUB"] = "gpus=8,mig=7"
+    env["ASAN_OPTIONS"] += ":detect_leaks=0" if which == "tsan" else ""
+    uri = "cuda:probe=off,cdi=nvidia.com/gpu,sysroot=" + tm._sysroot(tmp_path, 8, 7)
+    r = subprocess.run([bins[which], "threads", uri, "4", "3"], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-6000:])
+    assert "threads ok" in r.stdout and " 0 mismatching passes, 0 failures" in r.stdout
+    assert "Sanitizer" not in r.stderr and "runtime error" not in r.stderr
 
 
 @pytest.mark.parametrize("san", ["address,undefined", "thread"])
