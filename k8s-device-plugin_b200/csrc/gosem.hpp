@@ -16,6 +16,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -30,13 +31,19 @@ inline bool read_file(const std::string& path, std::string& out) {
     int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
     if (fd < 0) return false;
     out.clear();
+    // The read() that would only return 0 is skipped when fstat vouches for the size and it has all been read (regular
+    // files: fixture trees, tmpfs).  sysfs attributes claim a page and hold less, seq_file-backed files (debugfs
+    // amdgpu_firmware_info, /proc) claim 0 and may return short reads before EOF: those are read until read() returns
+    // 0, like Go's os.ReadFile -- a short read alone never means EOF.
+    struct stat st;
+    const bool size_known = ::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
     char buf[4096];
     for (;;) {
         ssize_t r = ::read(fd, buf, sizeof buf);
-        if (r < 0) { ::close(fd); return false; }
+        if (r < 0) { if (errno == EINTR) continue; ::close(fd); return false; }
         if (r == 0) break;
         out.append(buf, (size_t)r);
-        if ((size_t)r < sizeof buf) break;  // short read of a regular/sysfs file = EOF: saves the extra read() per file
+        if (size_known && out.size() >= (size_t)st.st_size) break;
     }
     ::close(fd);
     return true;

@@ -12,6 +12,7 @@
 #pragma once
 #include <poll.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/stat.h>
 #include <sys/un.h>
 #include <unistd.h>
@@ -258,7 +259,12 @@ inline bool grpc_unframe(const std::string& body, std::vector<std::string>& msgs
 // writes may come from any thread and are serialised here, DATA subject to the peer's flow-control windows.
 class Conn {
 public:
-    explicit Conn(int fd) : fd_(fd) {}
+    explicit Conn(int fd) : fd_(fd) {
+        // a peer that stops reading must not wedge a writer (which holds wmu_, and with it the reader's SETTINGS / PING
+        // acknowledgements) for ever: a send that makes no progress for 10 s fails and the connection is dropped
+        struct timeval tv{10, 0};
+        ::setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
+    }
     ~Conn() { close_fd(); }
     Conn(const Conn&) = delete;
     Conn& operator=(const Conn&) = delete;
@@ -347,7 +353,10 @@ public:
         } while (off < data.size());
         return true;
     }
+    // A stream this endpoint is serving / has opened: only those have a send window that WINDOW_UPDATE may move.
+    void open_stream(uint32_t stream) { std::lock_guard<std::mutex> l(wmu_); stream_window_.emplace(stream, peer_initial_window_); }
     void forget_stream(uint32_t stream) { std::lock_guard<std::mutex> l(wmu_); stream_window_.erase(stream); }
+    size_t tracked_streams() { std::lock_guard<std::mutex> l(wmu_); return stream_window_.size(); }
 
     // Bookkeeping for frames every endpoint must answer.  Returns false on a connection error.
     bool handle_control(const Frame& f) {
@@ -381,7 +390,12 @@ public:
             {
                 std::lock_guard<std::mutex> l(wmu_);
                 if (f.stream == 0) conn_window_ += inc;
-                else stream_window_locked(f.stream) += inc;
+                else {
+                    // RFC 9113 5.1: WINDOW_UPDATE may arrive for a stream that is already closed (or was never opened by
+                    // a confused peer) and is then ignored -- it must not create bookkeeping that nothing ever erases
+                    auto it = stream_window_.find(f.stream);
+                    if (it != stream_window_.end()) it->second += inc;
+                }
             }
             wcv_.notify_all();
             return true;
@@ -577,6 +591,7 @@ private:
             case F_HEADERS: case F_CONTINUATION: {
                 if (f.stream == 0) { ok = false; break; }
                 if (reqs.size() >= kMaxOpenRequests && !reqs.count(f.stream)) { ok = false; break; }  // a peer hoarding streams
+                if (!reqs.count(f.stream)) c->open_stream(f.stream);
                 Req& r = reqs[f.stream];
                 std::string frag;
                 if (f.type == F_HEADERS) { if (!Conn::strip(f, frag)) { ok = false; break; } }
@@ -691,6 +706,7 @@ inline Status unary_call_unix(const std::string& sock_path, const std::string& m
     Conn c(fd);
     if (!c.write_preface() || !c.write_frame(F_SETTINGS, 0, 0, "")) return {GRPC_UNAVAILABLE, "write failed"};
     const uint32_t sid = 1;
+    c.open_stream(sid);
     if (!c.send_headers(sid, {{":method", "POST"}, {":scheme", "http"}, {":path", method_path}, {":authority", "localhost"},
                               {"content-type", "application/grpc"}, {"te", "trailers"}, {"user-agent", "b200dp-plugind"}}, false))
         return {GRPC_UNAVAILABLE, "write failed"};
@@ -754,6 +770,7 @@ public:
             return {GRPC_UNAVAILABLE, e};
         }
         conn_ = std::make_unique<Conn>(fd);
+        conn_->open_stream(sid_);
         if (!conn_->write_preface() || !conn_->write_frame(F_SETTINGS, 0, 0, "") ||
             !conn_->send_headers(sid_, {{":method", "POST"}, {":scheme", "http"}, {":path", method_path}, {":authority", "localhost"},
                                         {"content-type", "application/grpc"}, {"te", "trailers"}}, false) ||

@@ -2,20 +2,32 @@
 // of cmd/k8s-device-plugin/main.go:93-155, one v1beta1.DevicePlugin gRPC server per resource on
 // <plugin_dir>/<namespace>_<name>, registration with the kubelet, the `-pulse` heartbeat ticker, and dpm's
 // lifecycle (vendor/github.com/kubevirt/device-plugin-manager/pkg/dpm): plugin start retried 3 times 3 s apart
-// (manager.go:16-20,205-219), re-serve + re-register when kubelet.sock is re-created (manager.go:73-84; polled
-// once a second instead of fsnotify), clean stop on SIGINT/SIGQUIT/SIGTERM (manager.go:47-48,85-91).
+// (manager.go:16-20,205-219), re-serve + re-register when kubelet.sock is created and stop serving when it is removed
+// (manager.go:73-84: inotify on the plugin directory, dpm's fsnotify watcher; a once-a-second stat of the socket stays
+// as the fallback where inotify is unavailable), clean stop on SIGINT/SIGQUIT/SIGTERM (manager.go:47-48,85-91).
 // gRPC comes from host/h2grpc.hpp; every RPC body is one C-ABI call (include/b200dp.h).
 //
 //   b200dp_plugind -pulse=10 -resource_naming_strategy=single -backend=cuda:xid=1 [-plugin_dir DIR]
 //   kill -USR1 <pid>     one heartbeat now
+//
+// Node-labeller mode (cmd/k8s-node-labeller/main.go:383-479 without the controller-runtime client), so the labeller
+// DaemonSet needs no Python:
+//   b200dp_plugind -labels=vram,cu-count,product-name [-backend=cuda:]       the label map as JSON
+//   b200dp_plugind -labels=all -reconcile < node-labels.json                 controller.go:23-58 on that map
+//   b200dp_plugind -labels=all -patch < node-labels.json                     the JSON merge patch for `kubectl patch node`
 #include <signal.h>
+#include <sys/inotify.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <iostream>
+#include <iterator>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -38,6 +50,8 @@ struct Flags {
     int link_check = 0;
     std::string exporter_socket;                     // optional: serve metricssvc.MetricsService here (health.go:36)
     bool version = false;
+    bool labels_mode = false, reconcile = false, patch = false;
+    std::string labels;                              // csv of generator names, or "all"
 };
 
 // Go's flag package: -name=value, -name value, --name...; bools not needed here
@@ -46,6 +60,9 @@ bool parse_flags(int argc, char** argv, Flags& f, std::string& err) {
         std::string a = argv[i];
         if (a.rfind("--", 0) == 0) a = a.substr(1);
         if (a == "-version") { f.version = true; continue; }
+        if (a == "-labels") { f.labels_mode = true; f.labels = "all"; continue; }
+        if (a == "-reconcile") { f.reconcile = true; continue; }
+        if (a == "-patch") { f.patch = true; continue; }
         if (a.empty() || a[0] != '-') { err = "unexpected argument " + a; return false; }
         std::string name = a.substr(1), val;
         const size_t eq = name.find('=');
@@ -67,6 +84,7 @@ bool parse_flags(int argc, char** argv, Flags& f, std::string& err) {
         else if (name == "start_retry_wait") f.start_retry_wait = atof(val.c_str());
         else if (name == "link_check") f.link_check = atoi(val.c_str());
         else if (name == "exporter_socket") f.exporter_socket = val;
+        else if (name == "labels") { f.labels_mode = true; f.labels = val; }
         else { err = "flag provided but not defined: -" + name; return false; }
     }
     if (!f.plugin_dir.empty() && f.plugin_dir.back() != '/') f.plugin_dir += '/';
@@ -335,6 +353,128 @@ void sleep_interruptible(double seconds) {
     }
 }
 
+
+// ---- node-labeller mode ---------------------------------------------------------------------------------------------
+// A flat JSON object of strings (a node's .metadata.labels): parser and writer.  null values are read as absent.
+void json_escape(std::string& o, const std::string& v) {
+    o.push_back('"');
+    for (unsigned char ch : v) {
+        if (ch == '"' || ch == '\\') { o.push_back('\\'); o.push_back((char)ch); }
+        else if (ch < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", ch); o += b; }
+        else o.push_back((char)ch);
+    }
+    o.push_back('"');
+}
+bool json_string(const std::string& s, size_t& i, std::string& out) {
+    if (i >= s.size() || s[i] != '"') return false;
+    out.clear();
+    for (++i; i < s.size(); ++i) {
+        const char ch = s[i];
+        if (ch == '"') { ++i; return true; }
+        if (ch != '\\') { out.push_back(ch); continue; }
+        if (++i >= s.size()) return false;
+        switch (s[i]) {
+            case 'n': out.push_back('\n'); break; case 't': out.push_back('\t'); break; case 'r': out.push_back('\r'); break;
+            case 'b': out.push_back('\b'); break; case 'f': out.push_back('\f'); break;
+            case 'u': {
+                if (i + 4 >= s.size()) return false;
+                const unsigned cp = (unsigned)strtoul(s.substr(i + 1, 4).c_str(), nullptr, 16);
+                i += 4;
+                if (cp < 0x80) out.push_back((char)cp);
+                else if (cp < 0x800) { out.push_back((char)(0xc0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 0x3f))); }
+                else { out.push_back((char)(0xe0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3f))); out.push_back((char)(0x80 | (cp & 0x3f))); }
+                break;
+            }
+            default: out.push_back(s[i]);
+        }
+    }
+    return false;
+}
+bool json_flat_object(const std::string& s, std::map<std::string, std::string>& out) {
+    size_t i = 0;
+    auto ws = [&] { while (i < s.size() && isspace((unsigned char)s[i])) ++i; };
+    ws();
+    if (s.compare(i, 4, "null") == 0) return true;  // a nil label map (controller.go:33-35)
+    if (i >= s.size() || s[i] != '{') return false;
+    ++i;
+    ws();
+    if (i < s.size() && s[i] == '}') return true;
+    for (;;) {
+        std::string k, v;
+        ws();
+        if (!json_string(s, i, k)) return false;
+        ws();
+        if (i >= s.size() || s[i] != ':') return false;
+        ++i;
+        ws();
+        if (s.compare(i, 4, "null") == 0) i += 4;
+        else { if (!json_string(s, i, v)) return false; out[k] = v; }
+        ws();
+        if (i < s.size() && s[i] == ',') { ++i; continue; }
+        return i < s.size() && s[i] == '}';
+    }
+}
+
+int labels_main(const Flags& fl) {
+    std::string uri = fl.backend;
+    // labels need no HBM ring and no CUDA context: NVML answers (probe=off) unless the operator chose a probe mode
+    if (uri.compare(0, 5, "cuda:") == 0 && uri.find("probe=") == std::string::npos) uri += (uri.size() > 5 ? "," : "") + std::string("probe=off");
+    b2dp_ctx* ctx = nullptr;
+    int rc = b2dp_open(uri.c_str(), &ctx);
+    if (rc != B2DP_OK && uri != fl.backend) rc = b2dp_open(fl.backend.c_str(), &ctx);  // no NVML: the in-process backend answers from CUDA
+    if (rc != B2DP_OK) { logf("open %s: %s (%s)", uri.c_str(), b2dp_strerror(rc), b2dp_last_error(nullptr)); return 1; }
+    std::string csv = fl.labels;
+    if (csv == "all") {  // main.go:46-53: every generator (+ the p2p-link extension on the cuda backend)
+        char names[16][64];
+        int n = 0;
+        b2dp_label_generator_names(names, 16, &n);
+        csv.clear();
+        for (int i = 0; i < n; ++i) csv += (i ? "," : "") + std::string(names[i]);
+        if (fl.backend.compare(0, 5, "cuda:") == 0) csv += ",p2p-link";
+    }
+    std::vector<b2dp_label> labels(256);
+    int n = 0;
+    rc = b2dp_generate_labels(ctx, csv.c_str(), labels.data(), (int)labels.size(), &n);
+    if (rc == B2DP_E_NOSPC) { labels.resize((size_t)n); rc = b2dp_generate_labels(ctx, csv.c_str(), labels.data(), n, &n); }
+    if (rc != B2DP_OK) { logf("generate labels: %s (%s)", b2dp_strerror(rc), b2dp_last_error(ctx)); b2dp_close(ctx); return 1; }
+    b2dp_close(ctx);
+    std::map<std::string, std::string> gen, before, after;
+    for (int i = 0; i < n; ++i) gen[labels[(size_t)i].key] = labels[(size_t)i].value;
+    auto dump = [](const std::map<std::string, std::string>& m) {
+        std::string o = "{";
+        bool first = true;
+        for (auto& kv : m) { if (!first) o += ","; first = false; json_escape(o, kv.first); o += ":"; json_escape(o, kv.second); }
+        return o + "}";
+    };
+    if (!fl.reconcile && !fl.patch) { printf("%s\n", dump(gen).c_str()); return 0; }
+    const std::string in((std::istreambuf_iterator<char>(std::cin)), std::istreambuf_iterator<char>());
+    if (!json_flat_object(in, before)) { logf("stdin is not a JSON object of strings (the node's label map)"); return 2; }
+    // controller.go:23-58: drop this labeller's old labels (main.go:55-74), then set the generated ones
+    std::vector<b2dp_label> cur(before.size() + 1);
+    size_t k = 0;
+    for (auto& kv : before) { snprintf(cur[k].key, sizeof cur[k].key, "%s", kv.first.c_str()); snprintf(cur[k].value, sizeof cur[k].value, "%s", kv.second.c_str()); ++k; }
+    int kept = 0;
+    b2dp_remove_old_node_labels(cur.data(), (int)before.size(), &kept);
+    for (int i = 0; i < kept; ++i) after[cur[(size_t)i].key] = before[cur[(size_t)i].key];  // values verbatim (the ABI field is 96 bytes)
+    for (auto& kv : gen) after[kv.first] = kv.second;
+    if (fl.reconcile) { printf("%s\n", dump(after).c_str()); return 0; }
+    // RFC 7386 merge patch: changed / new labels carry their value, removed ones null
+    std::string o = "{\"metadata\":{\"labels\":{";
+    bool first = true;
+    std::map<std::string, const std::string*> diff;
+    for (auto& kv : after) { auto it = before.find(kv.first); if (it == before.end() || it->second != kv.second) diff[kv.first] = &kv.second; }
+    for (auto& kv : before) if (!after.count(kv.first)) diff[kv.first] = nullptr;
+    for (auto& kv : diff) {
+        if (!first) o += ",";
+        first = false;
+        json_escape(o, kv.first);
+        o += ":";
+        if (kv.second) json_escape(o, *kv.second); else o += "null";
+    }
+    printf("%s}}}\n", o.c_str());
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -345,6 +485,7 @@ int main(int argc, char** argv) {
         printf("b200dp_plugind: libb200dp ABI %d (header %d), built %s\n", b2dp_abi_version(), B2DP_ABI_VERSION, __DATE__);
         return 0;
     }
+    if (fl.labels_mode) return labels_main(fl);
     if (fl.strategy != "single" && fl.strategy != "mixed") {  // main.go:42-51,113-117
         logf("invalid resource naming strategy: %s", fl.strategy.c_str());
         return 1;
@@ -395,6 +536,11 @@ int main(int argc, char** argv) {
     start_all();
 
     const std::string kubelet_sock = fl.plugin_dir + "kubelet.sock";
+    // dpm/manager.go:52-58,73-84: an fsnotify watcher on the plugin directory; Create of kubelet.sock (re)starts the
+    // plugin servers and re-registers, Remove stops them
+    const int ino_fd = inotify_init1(IN_NONBLOCK | IN_CLOEXEC);
+    const int ino_wd = ino_fd >= 0 ? inotify_add_watch(ino_fd, fl.plugin_dir.c_str(), IN_CREATE | IN_MOVED_TO | IN_DELETE | IN_MOVED_FROM) : -1;
+    if (ino_wd < 0) logf("inotify on %s unavailable: falling back to a once-a-second check of kubelet.sock", fl.plugin_dir.c_str());
     ino_t seen_ino = 0;
     long long seen_ctime = 0;
     bool have_seen = sock_identity(kubelet_sock, seen_ino, seen_ctime);
@@ -417,7 +563,30 @@ int main(int argc, char** argv) {
             next_beat += std::chrono::seconds(fl.pulse);
             heartbeat();
         }
-        if (now >= next_check) {  // dpm/manager.go:73-84: the kubelet restarted -> serve again and re-register
+        if (ino_wd >= 0) {
+            alignas(struct inotify_event) char evbuf[4096];
+            bool created = false, removed = false;
+            for (;;) {
+                const ssize_t r = read(ino_fd, evbuf, sizeof evbuf);
+                if (r <= 0) break;
+                for (char* p = evbuf; p < evbuf + r;) {
+                    const struct inotify_event* ev = reinterpret_cast<const struct inotify_event*>(p);
+                    if (ev->len && strcmp(ev->name, "kubelet.sock") == 0) {
+                        if (ev->mask & (IN_CREATE | IN_MOVED_TO)) { created = true; removed = false; }
+                        if (ev->mask & (IN_DELETE | IN_MOVED_FROM)) { removed = true; created = false; }
+                    }
+                    p += sizeof(struct inotify_event) + ev->len;
+                }
+            }
+            if (removed) { logf("kubelet.sock removed: stopping plugin servers"); plugins.clear(); have_seen = false; }
+            if (created) {
+                logf("kubelet.sock created: restarting plugins");
+                start_all();
+                have_seen = sock_identity(kubelet_sock, seen_ino, seen_ctime);
+                next_check = now + std::chrono::seconds(1);
+            }
+        }
+        if (now >= next_check) {  // fallback / safety net for the same events (a missed or unavailable inotify)
             next_check = now + std::chrono::seconds(1);
             ino_t ino = 0;
             long long ct = 0;
@@ -429,6 +598,7 @@ int main(int argc, char** argv) {
         }
     }
     logf("Received signal, exiting");
+    if (ino_fd >= 0) close(ino_fd);
     plugins.clear();
     if (exporter) exporter->stop();
     b2dp_close(ctx);

@@ -85,6 +85,34 @@ int main() {
     CHECK(!h2::grpc_unframe(std::string("\x01\x00\x00\x00\x01x", 6), msgs));  // compressed flag
     CHECK(!h2::grpc_unframe(std::string("\x00\x00\x00\x00\x05x", 6), msgs));  // truncated
     CHECK(h2::percent_encode("a b%\n\xc3\xa9") == "a b%25%0A%C3%A9" && h2::percent_decode("a b%25%0A%C3%A9") == "a b%\n\xc3\xa9");
+    // flow-control bookkeeping: WINDOW_UPDATE for streams that are not open (closed long ago, or never opened by a
+    // confused or hostile peer) must not create entries nothing ever erases; open streams are tracked until forgotten
+    {
+        int sv[2];
+        CHECK(socketpair(AF_UNIX, SOCK_STREAM, 0, sv) == 0);
+        h2::Conn c(sv[0]);
+        h2::Frame f;
+        f.type = h2::F_WINDOW_UPDATE; f.flags = 0;
+        f.payload = std::string("\x00\x00\x10\x00", 4);
+        for (uint32_t sid = 1; sid < 20001; sid += 2) { f.stream = sid; CHECK(c.handle_control(f)); }
+        CHECK(c.tracked_streams() == 0);
+        c.open_stream(7);
+        f.stream = 7;
+        CHECK(c.handle_control(f) && c.tracked_streams() == 1);
+        f.stream = 0;                       // connection-level credit is always taken
+        CHECK(c.handle_control(f) && c.tracked_streams() == 1);
+        c.forget_stream(7);
+        f.stream = 7;
+        CHECK(c.handle_control(f) && c.tracked_streams() == 0);
+        f.payload = "abc";                  // malformed: connection error
+        CHECK(!c.handle_control(f));
+        // a peer that never reads: the send times out (SO_SNDTIMEO set by Conn) instead of blocking for ever -- only
+        // checked for being configured, a 10 s stall has no place in a unit test
+        struct timeval tv{};
+        socklen_t len = sizeof tv;
+        CHECK(getsockopt(sv[0], SOL_SOCKET, SO_SNDTIMEO, &tv, &len) == 0 && tv.tv_sec == 10);
+        close(sv[1]);
+    }
     printf("%s\n", failed ? "FAIL" : "PASS");
     return failed ? 1 : 0;
 }

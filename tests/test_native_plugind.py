@@ -371,3 +371,48 @@ def test_native_kubelet_sim_drives_the_native_daemon():
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["resource"] == "amd.com/gpu" and d["iterations"] == 100 and d["response_bytes"] > 56 * 20
     assert 0 < d["heartbeat_to_kubelet_ms_median"] < 50
+
+
+def test_native_daemon_labeller_mode(daemon_env, pkg, monkeypatch, tmp_path):
+    """`b200dp_plugind -labels=...` is the node labeller without Python (cmd/k8s-node-labeller/main.go:383-479 minus
+    the controller-runtime client): the generated map equals the oracle's on the CPX capture; -reconcile applies
+    controller.go:23-58 to a node's label map read from stdin; -patch prints the JSON merge patch a K8s client sends."""
+    import json
+    from oracle import labeller as olab
+    V, root, plug_dir = daemon_env
+    gens = ["vram", "cu-count", "simd-count", "compute-memory-partition", "device-id", "driver-version"]
+    r = subprocess.run([EXE, "-labels=" + ",".join(gens), "-backend=kfd:" + root], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = olab.generateLabels({g: True for g in gens}, root)
+    assert json.loads(r.stdout) == want and want["amd.com/gpu.compute-memory-partition"] == "cpx_nps4"
+    node = {"keep": "me", "beta.amd.com/gpu.vram": "1G", "beta.amd.com/gpu.vram.1G": "8", "amd.com/gpu.cu-count": "7",
+            "quote\"d": "tab\there", "amd.com/gpu.compute-memory-partition": "cpx_nps4"}
+    r = subprocess.run([EXE, "-labels=" + ",".join(gens), "-reconcile", "-backend=kfd:" + root], input=json.dumps(node),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    after = olab.Reconcile(dict(node), want) if hasattr(olab, "Reconcile") else None
+    lab = pkg.labeller
+    assert json.loads(r.stdout) == lab.Reconcile(dict(node), dict(want)) and (after is None or after == json.loads(r.stdout))
+    r = subprocess.run([EXE, "-labels=" + ",".join(gens), "-patch", "-backend=kfd:" + root], input=json.dumps(node),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout) == json.loads(lab.node_label_merge_patch(node, lab.Reconcile(dict(node), dict(want))))
+    patch = json.loads(r.stdout)["metadata"]["labels"]
+    assert patch["beta.amd.com/gpu.vram.1G"] is None and "keep" not in patch and "amd.com/gpu.compute-memory-partition" not in patch
+    r = subprocess.run([EXE, "-labels=vram", "-patch", "-backend=kfd:" + root], input="[1,2]", capture_output=True, text=True)
+    assert r.returncode == 2 and "JSON object" in r.stderr
+    r = subprocess.run([EXE, "-labels=vram", "-reconcile", "-backend=kfd:" + root], input="null", capture_output=True, text=True)
+    assert r.returncode == 0 and json.loads(r.stdout) == olab.generateLabels({"vram": True}, root)
+    # `-labels` (all generators) on the cuda: backend needs neither a CUDA context nor an HBM ring: NVML answers
+    # (probe=off is implied) -- here a MIG-partitioned node described by the stand-in NVML
+    import test_mig_enumeration as tm
+    stub = tm.STUB
+    if not os.path.exists(stub):
+        pytest.skip("nvml stub not built (tests/test_mig_enumeration.py builds it)")
+    env = dict(os.environ, B2DP_NVML_LIBRARY=stub, B2DP_NVML_STUB="gpus=2,mig=3")
+    r = subprocess.run([EXE, "-labels", "-backend=cuda:sysroot=" + tm._sysroot(tmp_path, 2, 3)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    assert got["amd.com/gpu.compute-memory-partition"] == "1g_23gb" and got["amd.com/gpu.cu-count"] == "18"
+    assert got["amd.com/gpu.p2p-link"] == "nvlink" and got["amd.com/gpu.family"] == "Blackwell"
+    assert got["amd.com/gpu.driver-version"] == "580.159.03" and got["beta.amd.com/gpu.vram.23G"] == "6"

@@ -58,3 +58,33 @@ def test_link_reader_through_pair_weights(pkg, tmp_path, text):
     pol = pkg.allocator.NewBestEffortPolicy()
     err = pol.Init([pkg.allocator.Device(Id=d.Id, NodeId=d.NodeId, DevId=d.DevId, NumaNode=d.NumaNode) for d in odevs], root)
     assert err is None and pol.pair_weights() == want, text
+
+
+def test_read_to_eof_not_to_the_first_short_read(pkg, tmp_path):
+    """seq_file-backed files (debugfs amdgpu_firmware_info, /proc) may hand out short reads before EOF; Go's
+    os.ReadFile keeps reading until EOF and so must the reader (amdgpu.go:467-490).  A FIFO fed in small delayed
+    chunks stands in for such a file."""
+    import ctypes as C
+    import os
+    import threading
+    import time
+    N = pkg._native
+    lines = ["%s feature version: %d, firmware version: 0x%08x" % (name, i, 0x1000 + i)
+             for i, name in enumerate(["VCE", "UVD", "MC", "ME", "PFP", "CE", "RLC", "MEC", "SMC", "SDMA0"])]
+    fifo = str(tmp_path / "amdgpu_firmware_info")
+    os.mkfifo(fifo)
+
+    def feed():
+        with open(fifo, "w") as f:
+            for ln in lines:
+                f.write(ln + "\n")
+                f.flush()
+                time.sleep(0.01)
+    t = threading.Thread(target=feed)
+    t.start()
+    out = (N.FwEntry * 64)()
+    n = C.c_int(0)
+    rc = N.lib.b2dp_parse_debugfs_firmware_info(fifo.encode(), out, 64, C.byref(n))
+    t.join()
+    assert rc == 0 and n.value == len(lines)
+    assert sorted(e.name.decode() for e in out[:n.value]) == sorted(ln.split()[0] for ln in lines)
