@@ -832,7 +832,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         unsigned long long cmd = 0;
         if (L) {  // hand the other NUMA node's GPUs to the helper, then enqueue our own
             L->res = &res; L->state = &state; L->variant = variant;
-            cmd = L->cmd.fetch_add(1, std::memory_order_release) + 1;
+            cmd = L->cmd.fetch_add(1) + 1;  // seq_cst: ordered against the `sleeping` load below (store/load pair on both sides)
             if (L->sleeping.load()) { std::lock_guard<std::mutex> l(L->mu); L->cv.notify_one(); }
         }
         for (size_t i : be->caller_idx) {

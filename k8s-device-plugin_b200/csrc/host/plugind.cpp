@@ -416,6 +416,7 @@ bool json_flat_object(const std::string& s, std::map<std::string, std::string>& 
 }
 
 int labels_main(const Flags& fl) {
+    if (fl.ns != "amd.com" && b2dp_set_vendor_domain(fl.ns.c_str()) != B2DP_OK) { logf("bad -resource_namespace %s", fl.ns.c_str()); return 2; }
     std::string uri = fl.backend;
     // labels need no HBM ring and no CUDA context: NVML answers (probe=off) unless the operator chose a probe mode
     if (uri.compare(0, 5, "cuda:") == 0 && uri.find("probe=") == std::string::npos) uri += (uri.size() > 5 ? "," : "") + std::string("probe=off");

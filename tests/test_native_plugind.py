@@ -416,3 +416,33 @@ def test_native_daemon_labeller_mode(daemon_env, pkg, monkeypatch, tmp_path):
     assert got["amd.com/gpu.compute-memory-partition"] == "1g_23gb" and got["amd.com/gpu.cu-count"] == "18"
     assert got["amd.com/gpu.p2p-link"] == "nvlink" and got["amd.com/gpu.family"] == "Blackwell"
     assert got["amd.com/gpu.driver-version"] == "580.159.03" and got["beta.amd.com/gpu.vram.23G"] == "6"
+
+
+def test_deploy_manifests_use_flags_the_daemon_accepts():
+    """deploy/*.yaml and the Helm chart's values: every daemon argument parses (`-version` after them exits 0 only
+    if the flag parser accepted all of them), the backend URIs are well-formed option lists, and the chart carries the
+    reference chart's four templates (helm/amd-gpu/templates)."""
+    import re
+    import yaml
+    dep = os.path.join(ROOT, "deploy")
+    seen = 0
+    for fn in ("k8s-ds-b200-dp-health.yaml", "k8s-ds-b200-labeller.yaml"):
+        for doc in yaml.safe_load_all(open(os.path.join(dep, fn))):
+            if not doc or doc.get("kind") != "DaemonSet":
+                continue
+            for c in doc["spec"]["template"]["spec"]["containers"]:
+                args = list(c.get("args", []))
+                assert c.get("command", ["/opt/b200dp/k8s-device-plugin_b200/b200dp_plugind"])[0].endswith("b200dp_plugind")
+                r = subprocess.run([EXE] + args + ["-version"], capture_output=True, text=True)
+                assert r.returncode == 0, (fn, args, r.stderr)
+                for a in args:
+                    if a.startswith("-backend=cuda:"):
+                        assert re.fullmatch(r"-backend=cuda:([a-z_]+=[^,]+(,[a-z_]+=[^,]+)*)?", a), a
+                seen += 1
+    assert seen == 2
+    chart = os.path.join(dep, "helm", "b200-gpu")
+    vals = yaml.safe_load(open(os.path.join(chart, "values.yaml")))
+    assert vals["labeller"]["enabled"] is False and vals["dp"]["pulse"] == 10 and "min_frac=0.8" in vals["dp"]["backend"]
+    assert yaml.safe_load(open(os.path.join(chart, "Chart.yaml")))["name"] == "b200-gpu"
+    for t in ("deviceplugin-daemonset.yaml", "labeller.yaml", "rbac.yaml", "serviceaccount.yaml", "_helpers.tpl", "NOTES.txt"):
+        assert os.path.exists(os.path.join(chart, "templates", t)), t
