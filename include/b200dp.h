@@ -155,6 +155,18 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     mig=auto|off (default auto): with MIG mode enabled on a GPU (NVML), its MIG devices are enumerated
  *                     instead of the GPU (ids "nvidia_mig_<gpu>_<gi>_<ci>", dev_id of the parent, partition strings
  *                     "<N>g"/"<M>gb") and probed by one helper process per instance.
+ *                     probe=inproc|helpers|off (default inproc): helpers = this process never creates a CUDA context; one
+ *                     b200dp_probe_helper child per listed unit (found next to libb200dp.so, or B2DP_PROBE_HELPER), started
+ *                     with CUDA_VISIBLE_DEVICES=<unit UUID>, runs the same probe and answers over a socketpair; a child that
+ *                     dies is reported Unhealthy (B2DP_E_CUDA) and restarted by the next pass; link classes are declared
+ *                     from NVML (no cross-process P2P measurement).  off = enumeration / allocation / labels only (NVML,
+ *                     no CUDA, no HBM ring: what a labeller needs); the probe entry points return B2DP_E_UNSUPPORTED.
+ *                     mig_bytes=<ring slot on a MIG instance, default 268435456>.
+ *                     launchers=1|2 (default 1): 2 = a helper thread enqueues the passes of the GPUs on the other NUMA
+ *                     node while the caller enqueues its own (spin_us=<how long it keeps spinning after a fan-out or a
+ *                     pre-arm, default 500>); measured neutral at 8 GPUs (the driver serialises launches), so off by
+ *                     default.  pin=1: bind the calling thread of the fan-out to the CPUs local to its GPUs.
+ *                     seed_index=<i>: (helpers) the enumeration index this one-device context stands for.
  *                     A GPU whose own setup fails (or that break=<i>+<j>, a test hook, names by enumeration index)
  *                     stays in the device list and is reported Unhealthy with B2DP_E_CUDA on every pass; the open
  *                     only fails when no GPU could be set up.

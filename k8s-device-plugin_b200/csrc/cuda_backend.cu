@@ -147,6 +147,7 @@ public:
     std::mutex probe_mu;  // one fan-out at a time
     std::mutex bc_mu;
     std::unique_ptr<UnitsBackend> units;             // probe=helpers / probe=off / MIG: the NVML-driven half (units_backend.hpp)
+    std::vector<std::unique_ptr<std::atomic<unsigned long long>>> unit_xid;  // xid=1 in units mode: one sticky latch per unit
     std::unique_ptr<Launcher> launcher;              // launchers=2
     std::vector<size_t> caller_idx;                  // the GPUs the calling thread enqueues (all of them without a launcher)
     cpu_set_t caller_cpus;                           // pin=1: CPUs local to the caller's GPUs
@@ -375,6 +376,18 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         }
         if (be->driver_version.empty()) be->driver_version = read_trim(go::join(cfg.sysroot, "sys/module/nvidia/version"));
         be->driver_src_version = read_trim(go::join(cfg.sysroot, "sys/module/nvidia/srcversion"));
+        for (size_t i = 0; i < be->units->units.size(); ++i) be->unit_xid.push_back(std::make_unique<std::atomic<unsigned long long>>(0));
+        // xid=1 needs no CUDA: NVML delivers critical Xid events to this process for the physical GPUs the units live on
+        if (cfg.check_xid && be->nvml.event_set_create && be->nvml.register_events && be->nvml.event_wait &&
+            be->nvml.event_set_create(&be->xid_set) == 0) {
+            std::vector<void*> seen;
+            for (auto& u : be->units->units)
+                if (u.nvh && std::find(seen.begin(), seen.end(), u.nvh) == seen.end()) {
+                    seen.push_back(u.nvh);
+                    be->nvml.register_events(u.nvh, 0x8ull /*nvmlEventTypeXidCriticalError*/, be->xid_set);
+                }
+            be->xid_thread = std::thread(xid_listener, be.get());
+        }
         *out = be.release();
         return B2DP_OK;
     }
@@ -632,7 +645,15 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
 
 void cuda_backend_close(CudaBackend* be) {
     if (!be) return;
-    if (be->units) { units_close(be->units.get()); delete be; return; }
+    if (be->units) {
+        be->xid_quit = true;
+        if (be->xid_thread.joinable()) be->xid_thread.join();
+        { std::lock_guard<std::mutex> l(be->xid_cb_mu); be->on_health_event = nullptr; }
+        units_close(be->units.get());
+        if (be->xid_set && be->nvml.event_set_free) be->nvml.event_set_free(be->xid_set);
+        delete be;
+        return;
+    }
     be->xid_quit = true;
     if (be->xid_thread.joinable()) be->xid_thread.join();
     { std::lock_guard<std::mutex> l(be->xid_cb_mu); be->on_health_event = nullptr; }
@@ -753,6 +774,15 @@ static void xid_listener(CudaBackend* be) {
         bool hit = false;
         for (auto& g : be->gpus)
             if (g->nvh == d.device && !xid_is_application_error(d.data)) { latch_xid(g.get(), d.data); hit = true; }
+        if (be->units && !xid_is_application_error(d.data))
+            for (size_t i = 0; i < be->units->units.size(); ++i) {
+                const Unit& u = be->units->units[i];
+                // a MIG-attributed Xid names its GPU instance; 0xFFFFFFFF = the whole GPU (every instance on it)
+                if (u.nvh != d.device || (u.mig_slot >= 0 && d.gi != 0xffffffffu && d.gi != u.gi)) continue;
+                unsigned long long none = 0;
+                be->unit_xid[i]->compare_exchange_strong(none, d.data ? d.data : 999);
+                hit = true;
+            }
         if (hit) be->fire_health_event();
     }
 }
@@ -761,7 +791,11 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     std::lock_guard<std::mutex> pl(be->probe_mu);
     if (be->units) {
         if (!be->units->helpers) { err = "probe=off: this context enumerates only"; return B2DP_E_UNSUPPORTED; }
-        return units_probe(be->units.get(), opts, out, err);
+        const int rc = units_probe(be->units.get(), opts, out, err);
+        if (rc == B2DP_OK && be->cfg.check_xid)
+            for (size_t i = 0; i < out.size() && i < be->unit_xid.size(); ++i)
+                if (be->unit_xid[i]->load()) { out[i].flags |= B2DP_RES_XID; out[i].healthy = 0; be->units->units[i].last_healthy = 0; }
+        return rc;
     }
     int rc = B2DP_OK;
     const uint32_t variant = opts ? (opts->flags & B2DP_PROBE_VARIANT_MASK) : 0;
@@ -991,6 +1025,15 @@ static int units_forward(CudaBackend* be, int device, HelperReq q, std::string& 
 }
 
 int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask, std::string& err) {
+    if (be->units && word == ~0ull) {  // synthetic critical Xid, as in the in-process mode below
+        if (device < 0 || device >= (int)be->unit_xid.size()) { err = "device index out of range"; return B2DP_E_INVAL; }
+        if (be->cfg.check_xid && !xid_is_application_error(mask)) {
+            unsigned long long none = 0;
+            be->unit_xid[device]->compare_exchange_strong(none, mask ? mask : 999);
+            be->fire_health_event();
+        }
+        return B2DP_OK;
+    }
     if (be->units) {
         std::lock_guard<std::mutex> pl(be->probe_mu);
         HelperReq q{};
@@ -1025,7 +1068,9 @@ int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
     std::lock_guard<std::mutex> pl(be->probe_mu);
     if (be->units) {
         for (int i = 0; i < (int)be->units->units.size(); ++i) {
-            if ((device >= 0 && device != i) || be->units->units[i].broken) continue;
+            if (device >= 0 && device != i) continue;
+            be->unit_xid[i]->store(0);  // operator acknowledgement
+            if (be->units->units[i].broken || !be->units->helpers) continue;
             HelperReq q{};
             q.op = HOP_RESET;
             int rc = units_forward(be, i, q, err);

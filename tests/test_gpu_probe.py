@@ -603,6 +603,21 @@ def test_one_unusable_gpu_does_not_take_the_node_down(P):
         assert np.array_equal(ctx.probe_peek(0, 0, 16), oprobe.pattern(16, oprobe.next_seed(oprobe.next_seed(oprobe.initial_seed(0)))))
         gbs, lt, mm = ctx.p2p_matrix()
         assert lt[0][1] == 0 and lt[1][0] == 0                        # no link measured to or from the broken GPU
+    # the FIRST GPU (lowest BDF) is the broken one: nothing may depend on device 0 being usable -- the checksum
+    # reference is the host's closed form, not a kernel on gpus[0] (round-1 advisor finding)
+    with P.Context("cuda:devices=0+1,bytes=%d,p2p_bytes=%d,break=0" % (64 * MiB, 16 * MiB)) as ctx:
+        ids = sorted(ctx.enumerate())
+        for _ in range(2):
+            res = ctx.probe_health(min_gbs=1e-3)
+            assert [(r.healthy, r.err) for r in res] == [(False, P._native.E_CUDA), (True, 0)] and res[0].bytes == 0
+            assert res[1].checksum == res[1].expected_checksum == oprobe.expected_checksum(64 * MiB // 4, res[1].seed)
+        wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT, min_gbs=1e-3)
+        msg = P.v1beta1.ListAndWatchResponse.FromString(wire)
+        assert [(d.ID, d.health) for d in msg.devices] == [(ids[0], "Unhealthy"), (ids[1], "Healthy")]
+        gbs, lt, mm = ctx.p2p_matrix()                                # does not fail: the matrix simply has no link to GPU 0
+        assert lt[0][1] == 0 and lt[1][0] == 0 and (mm == 0).all()
+        ctx.start()                                                   # allocator init degrades (no weights), never crashes
+        assert ctx.generate_labels(["vram", "cu-count"])["amd.com/gpu.cu-count"] == "148"
 
 
 def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
@@ -765,6 +780,17 @@ def test_probe_through_helper_processes(P):
         assert all(r.err == 0 and r.healthy for r in res)
     time.sleep(0.3)
     assert subprocess_pids_of_helpers() == []                       # closing the context reaps every child
+    # xid=1 works without CUDA in the parent: NVML delivers critical Xids for the physical GPU (synthetic events here)
+    UINT64_MAX = (1 << 64) - 1
+    with P.Context("cuda:probe=helpers,devices=0,bytes=%d,xid=1" % (16 * MiB)) as x:
+        assert x.probe_health(min_gbs=1e-3)[0].healthy
+        x.probe_inject_fault(0, UINT64_MAX, 31)                      # application-level: ignored
+        assert x.probe_health(min_gbs=1e-3)[0].healthy
+        x.probe_inject_fault(0, UINT64_MAX, 79)                      # fallen off the bus
+        (r,) = x.probe_health(min_gbs=1e-3)
+        assert not r.healthy and r.flags & P._native.RES_XID and r.mismatches == 0 and r.checksum == r.expected_checksum
+        x.probe_reset(0)
+        assert x.probe_health(min_gbs=1e-3)[0].healthy
 
 
 def subprocess_pids_of_helpers():
