@@ -78,3 +78,39 @@ def test_reference_arm_does_not_load_the_product():
             % os.path.join(ROOT, "bench.py"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert "PRODUCT_SO=0" in r.stderr and "PRODUCT_PKG=0" in r.stderr, r.stderr[-2000:]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N>1: the driver launches both arms with torchrun; in the CPU arm rank 0 alone works and prints, the other rank
+    exits 0 without a line."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["config"]["n_devices"] == 2 and d["value"] > 0
+
+
+def test_file_flag_releases_the_waiting_ranks(tmp_path, monkeypatch):
+    """bench.py's rank-0-alone leg: the other ranks sleep on a file, not on an NCCL barrier."""
+    import threading
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setenv("MASTER_PORT", "29534")
+    monkeypatch.setenv("TORCHELASTIC_RUN_ID", "t%d" % os.getpid())
+    a, b = bench.FileFlag(), bench.FileFlag()
+    assert a.path == b.path
+    a.clear()
+    t0 = time.time()
+    th = threading.Thread(target=lambda: (time.sleep(0.2), a.set()))
+    th.start()
+    b.wait(timeout=10)
+    th.join()
+    assert 0.15 < time.time() - t0 < 5
+    a.clear()
+    import pytest
+    with pytest.raises(SystemExit):
+        b.wait(timeout=0.1)

@@ -730,8 +730,10 @@ def test_probe_through_helper_processes(P):
     n = torch.cuda.device_count()
     nbytes = 192 * MiB + 16 * 11
     n_words = nbytes // 4
-    with P.Context("cuda:probe=helpers,bytes=%d" % nbytes) as ctx, P.Context("cuda:bytes=%d,calib=0" % MiB) as direct:
-        assert ctx.enumerate() == direct.enumerate()                 # same table as the in-process backend
+    with P.Context("cuda:bytes=%d,calib=0" % MiB) as direct:
+        direct_table = direct.enumerate()
+    with P.Context("cuda:probe=helpers,bytes=%d" % nbytes) as ctx:
+        assert ctx.enumerate() == direct_table                       # same table as the in-process backend
         info = P._native.ProbeInfo()
         for i in range(n):
             assert P._native.lib.b2dp_probe_describe(ctx._h, i, info) == 0
@@ -759,6 +761,13 @@ def test_probe_through_helper_processes(P):
         ctx.probe_set_ref(0, 1e6)                                    # a ceiling no part reaches: below the 0.8 line
         res = ctx.probe_health(timed=False)
         assert not res[0].healthy and res[0].flags & P._native.RES_SLOW and all(r.healthy for r in res[1:])
+        assert not (res[0].flags & P._native.RES_CONTENDED)          # the helper is the only process on its GPU
+        # ... whereas a slow pass on a GPU that ANOTHER process is using is not a verdict on the part: with a second
+        # context (this process, in-process backend) on the same GPU, NVML lists two compute processes -> CONTENDED
+        with P.Context("cuda:devices=0,bytes=%d,calib=0" % MiB):
+            res = ctx.probe_health(timed=False)
+            if res[0].flags & P._native.RES_CONTENDED:               # needs NVML process accounting in this container
+                assert res[0].healthy and res[0].flags & P._native.RES_SLOW and res[0].mismatches == 0
         ctx.probe_set_ref(0, 0.0)
         assert all(r.healthy for r in ctx.probe_health(timed=False))
         # Start(): no CUDA here, so the link classes are declared from NVML (NVLink on an HGX board), not measured
