@@ -141,6 +141,14 @@ class Context:
         """Pin the bandwidth ceiling the fractional floor refers to (<= 0: back to the device's own calibration)."""
         N.check(N.lib.b2dp_probe_set_ref(self._h, device, gbs_ref), self._h)
 
+    def probe_describe(self, device: int) -> dict:
+        """Ring geometry, calibrated ceiling and runtime identity of `device` (b2dp_probe_describe); no pass runs."""
+        info = N.ProbeInfo()
+        N.check(N.lib.b2dp_probe_describe(self._h, device, C.byref(info)), self._h)
+        return {"slot_bytes": info.slot_bytes, "total_memory": info.total_memory, "sm_count": info.sm_count,
+                "slots": info.slots, "gbs_cal": info.gbs_cal, "gbs_ref": info.gbs_ref, "usable": bool(info.usable),
+                "via_helper": bool(info.via_helper), "uuid": N.s(info.uuid), "name": N.s(info.name)}
+
     def probe_peek(self, device: int, word_index: int, n_words: int):
         import numpy as np
         out = np.empty(n_words, dtype=np.uint32)

@@ -73,9 +73,21 @@ def classify_link(can_access_peer: bool, gbs: float) -> int:
     return LINK_NVLINK if gbs >= NVLINK_CLASS_FRACTION * NVLINK_REF_GBS else LINK_PCIE
 
 
+MIN_FRAC = 0.8                 # BASELINE.json: "each per-GPU probe >= 80 % of HBM peak GB/s"
+FLOOR_MIN_BYTES = 128 << 20    # the fractional floor needs a ring slot above the 126 MB L2 (a pass that measures HBM)
+
+
+def health_floor(slot_bytes: int, gbs_ref: float, min_frac: float = MIN_FRAC, abs_min_gbs: float = 0.0) -> float:
+    """The GB/s floor of the product's verdict: an absolute `min_gbs` if one is given, else min_frac x the device's
+    calibrated ceiling when the ring streams from HBM, else none."""
+    if abs_min_gbs > 0:
+        return abs_min_gbs
+    return min_frac * gbs_ref if slot_bytes >= FLOOR_MIN_BYTES and gbs_ref > 0 else 0.0
+
+
 def probe_healthy(launch_ok: bool, got_checksum: int, mismatches: int, n_words: int, seed: int,
                   gbs: float, min_gbs: float) -> bool:
     """Verdict rule of the product: the launch completed, every word verified,
-    the checksum matches the closed form, and the stream ran at >= min_gbs."""
+    the checksum matches the closed form, and the stream ran at >= min_gbs (= health_floor(...))."""
     return bool(launch_ok and mismatches == 0 and got_checksum == expected_checksum(n_words, seed)
                 and gbs >= min_gbs)

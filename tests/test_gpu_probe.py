@@ -639,7 +639,9 @@ def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
                 assert r.healthy == want and abs(r.frac - frac) < 0.008, (frac, r)
                 assert r.mismatches == 0 and r.checksum == r.expected_checksum and r.err == 0
                 assert bool(r.flags & P._native.RES_SLOW) == (not want)
-                assert abs(r.min_gbs_applied - 0.8 * r.gbs_ref) < 1.0
+                assert abs(r.min_gbs_applied - oprobe.health_floor(nbytes, r.gbs_ref)) < 1.0    # the oracle's floor rule
+                assert r.healthy == oprobe.probe_healthy(True, r.checksum, r.mismatches, nbytes // 4, r.seed,
+                                                         r.frac * r.gbs_ref, r.min_gbs_applied)
         ctx.probe_set_ref(0, gbs / 0.79)
         wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT)
         assert [d.health for d in P.v1beta1.ListAndWatchResponse.FromString(wire).devices] == ["Unhealthy"]
@@ -669,6 +671,7 @@ def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
     with _open(P, 16 * MiB) as ctx:
         (r,) = ctx.probe_health(timed=False)
         assert r.healthy and r.flags & P._native.RES_NO_FLOOR and r.min_gbs_applied == 0.0 and r.gbs_ref > 0
+        assert oprobe.health_floor(16 * MiB, r.gbs_ref) == 0.0 and oprobe.health_floor(16 * MiB, r.gbs_ref, abs_min_gbs=5.0) == 5.0
         (r,) = ctx.probe_health(timed=False, min_gbs=1e9)
         assert not r.healthy and not (r.flags & P._native.RES_NO_FLOOR)
 
