@@ -81,7 +81,7 @@ void policy_free(BestEffortPolicy* p) { delete p; }
 static bool fetch_topo_properties(const std::string& path, const char* const* keys, int n_keys, int* res) {
     std::string data;
     for (int i = 0; i < n_keys; ++i) res[i] = 0;
-    if (!go::read_file(path, data)) return false;
+    if (!go::read_attr(path, data)) return false;
     bool ok = true;
     go::scan_lines(data, [&](std::string_view line) {
         for (int i = 0; i < n_keys; ++i) {

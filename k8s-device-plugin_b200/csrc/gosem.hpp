@@ -27,23 +27,37 @@ namespace b2dp {
 namespace go {
 
 // ---- files ---------------------------------------------------------------------------
+// os.ReadFile: read until read() returns 0.  seq_file-backed files (debugfs amdgpu_firmware_info, /proc), pipes and
+// the like may hand out short reads before EOF, so a short read alone never ends the loop.
 inline bool read_file(const std::string& path, std::string& out) {
     int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
     if (fd < 0) return false;
     out.clear();
-    // The read() that would only return 0 is skipped when fstat vouches for the size and it has all been read (regular
-    // files: fixture trees, tmpfs).  sysfs attributes claim a page and hold less, seq_file-backed files (debugfs
-    // amdgpu_firmware_info, /proc) claim 0 and may return short reads before EOF: those are read until read() returns
-    // 0, like Go's os.ReadFile -- a short read alone never means EOF.
-    struct stat st;
-    const bool size_known = ::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
     char buf[4096];
     for (;;) {
         ssize_t r = ::read(fd, buf, sizeof buf);
         if (r < 0) { if (errno == EINTR) continue; ::close(fd); return false; }
         if (r == 0) break;
         out.append(buf, (size_t)r);
-        if (size_known && out.size() >= (size_t)st.st_size) break;
+    }
+    ::close(fd);
+    return true;
+}
+// The hot parse path only (kfd topology `properties` files: sysfs attributes and their captured copies): an attribute
+// is at most one page and sysfs hands it out in a single read, a regular file only returns short at EOF -- so there a
+// short read IS the end and the read() that would return 0 is saved (one syscall less per file, ~4000 files per
+// pair-weight init on the CPX tree).  Same result as read_file on such files; never used for debugfs, /proc or pipes.
+inline bool read_attr(const std::string& path, std::string& out) {
+    int fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return false;
+    out.clear();
+    char buf[4096];
+    for (;;) {
+        ssize_t r = ::read(fd, buf, sizeof buf);
+        if (r < 0) { if (errno == EINTR) continue; ::close(fd); return false; }
+        if (r == 0) break;
+        out.append(buf, (size_t)r);
+        if ((size_t)r < sizeof buf) break;
     }
     ::close(fd);
     return true;

@@ -38,7 +38,7 @@ static void scan_first_match(std::string_view data, KeyHit* hits, int n_hits) {
 int kfd_parse_property(const std::string& path, const char* key, int64_t* value) {
     std::string data;
     *value = 0;
-    if (!go::read_file(path, data)) return B2DP_E_IO;
+    if (!go::read_attr(path, data)) return B2DP_E_IO;
     KeyHit h{key};
     scan_first_match(data, &h, 1);
     if (!h.found) return B2DP_E_NOTFOUND;
@@ -53,7 +53,7 @@ void kfd_topology_maps(const std::string& topo_root, TopoMaps& out) {
     out.node_ids.clear();
     std::string data;
     for (const auto& node_file : go::glob_node_properties(topo_root)) {
-        if (!go::read_file(node_file, data)) continue;
+        if (!go::read_attr(node_file, data)) continue;
         KeyHit h[3] = {{"drm_render_minor"}, {"location_id"}, {"domain"}};
         scan_first_match(data, h, 3);
         if (!h[0].found || h[0].err != go::NumErr::none) continue;  // amdgpu.go:118-122,513-517
@@ -76,7 +76,7 @@ void kfd_topology_maps(const std::string& topo_root, TopoMaps& out) {
 
 static bool read_trim_lower(const std::string& path, std::string& out) {
     std::string data;
-    if (!go::read_file(path, data)) return false;
+    if (!go::read_attr(path, data)) return false;
     out = go::to_lower(go::trim_space(data));
     return true;
 }
@@ -201,7 +201,7 @@ int kfd_count_gpu_dev(const std::string& topo_root) {
     int count = 0;  // plugin.go:123-159
     std::string data;
     for (const auto& f : go::glob_node_properties(topo_root)) {
-        if (!go::read_file(f, data)) continue;
+        if (!go::read_attr(f, data)) continue;
         go::scan_lines(data, [&](std::string_view line) {
             std::string_view digits;
             if (!go::match_key_digits(line, "simd_count", digits)) return true;
@@ -216,7 +216,7 @@ bool kfd_simple_health_check(const std::string& topo_root) {
     std::string data;  // plugin.go:161-206
     bool found = false;
     go::for_each_node_properties(topo_root, [&](const std::string& f) {
-        if (!go::read_file(f, data)) return true;
+        if (!go::read_attr(f, data)) return true;
         int64_t cpu_cores = 0, gfx = 0;
         auto starts = [](std::string_view l, const char* p) { return l.compare(0, strlen(p), p) == 0; };
         const bool scan_err = go::scan_lines(data, [&](std::string_view line) {
