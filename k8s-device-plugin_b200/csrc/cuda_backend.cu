@@ -567,7 +567,7 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
             }
             // Calibration: best of `calib` warm, non-advancing passes (read slot 0, write slot 1 un-re-keyed; seed and
             // ring position stay where they are) = what this device streams when healthy and idle.
-            for (int k = 0; k < calib + 1; ++k) {
+            for (int k = 0; k < (calib > 0 ? calib + 1 : 0); ++k) {
                 ProbeJobResult r;
                 r.advance = false;
                 r.timed = true;

@@ -763,14 +763,15 @@ def test_probe_through_helper_processes(P):
         assert st.n_devices == n and st.n_unhealthy == 0            # reported once; the helper re-filled its ring
         ctx.probe_set_ref(0, 1e6)                                    # a ceiling no part reaches: below the 0.8 line
         res = ctx.probe_health(timed=False)
-        assert not res[0].healthy and res[0].flags & P._native.RES_SLOW and all(r.healthy for r in res[1:])
-        assert not (res[0].flags & P._native.RES_CONTENDED)          # the helper is the only process on its GPU
-        # ... whereas a slow pass on a GPU that ANOTHER process is using is not a verdict on the part: with a second
-        # context (this process, in-process backend) on the same GPU, NVML lists two compute processes -> CONTENDED
-        with P.Context("cuda:devices=0,bytes=%d,calib=0" % MiB):
-            res = ctx.probe_health(timed=False)
-            if res[0].flags & P._native.RES_CONTENDED:               # needs NVML process accounting in this container
-                assert res[0].healthy and res[0].flags & P._native.RES_SLOW and res[0].mismatches == 0
+        assert res[0].flags & P._native.RES_SLOW and abs(res[0].min_gbs_applied - 0.8e6) < 1.0 and all(r.healthy for r in res[1:])
+        # A slow pass is a verdict on the part only if nothing else was using the GPU.  This pytest process has held a
+        # CUDA context on GPU 0 since the earlier in-process tests, so NVML lists two compute processes (it and the
+        # helper): the pass is flagged CONTENDED and judged on integrity alone.  Without process accounting (some
+        # containers) or with the helper alone on its GPU the verdict is Unhealthy.
+        if res[0].flags & P._native.RES_CONTENDED:
+            assert res[0].healthy and res[0].mismatches == 0 and res[0].checksum == res[0].expected_checksum
+        else:
+            assert not res[0].healthy
         ctx.probe_set_ref(0, 0.0)
         assert all(r.healthy for r in ctx.probe_health(timed=False))
         # Start(): no CUDA here, so the link classes are declared from NVML (NVLink on an HGX board), not measured
