@@ -333,7 +333,48 @@ static int cmd_threads(char** argv) {
     return g_fail ? 1 : 0;
 }
 
+// probe=helpers against whatever B2DP_PROBE_HELPER names (tests/native/fake_probe_helper.cpp): T threads run probe
+// fan-outs and heartbeat cycles on ONE context (the backend serialises fan-outs), children are spawned, fed and reaped.
+static int cmd_helpers(char** argv) {
+    const int T = atoi(argv[3]), iters = atoi(argv[4]);
+    b2dp_ctx* c = nullptr;
+    if (b2dp_open(argv[2], &c) != B2DP_OK) { fprintf(stderr, "open failed: %s\n", b2dp_last_error(nullptr)); return 2; }
+    Ids ids;
+    EXPECT(enumerate_all(c, ids) == B2DP_OK);
+    const int n = (int)ids.devs.size();
+    std::atomic<int> bad{0}, passes{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+            std::vector<b2dp_probe_result> res((size_t)n + 1);
+            std::vector<uint8_t> buf(1 << 14);
+            for (int i = 0; i < iters; ++i) {
+                int m = 0;
+                if ((i + t) % 2 == 0) {
+                    if (b2dp_probe_health(c, nullptr, res.data(), (int)res.size(), &m) != B2DP_OK || m != n) { bad++; continue; }
+                    for (int k = 0; k < m; ++k)
+                        if (!res[(size_t)k].healthy || res[(size_t)k].checksum != res[(size_t)k].expected_checksum || res[(size_t)k].device != k) bad++;
+                } else {
+                    b2dp_cycle_opts co{};
+                    co.flags = B2DP_LW_HEARTBEAT;
+                    size_t len = 0;
+                    b2dp_cycle_stats st{};
+                    if (b2dp_list_and_watch(c, "1g_23gb", &co, buf.data(), buf.size(), &len, &st) != B2DP_OK || st.n_devices != n || st.n_unhealthy) bad++;
+                }
+                passes++;
+            }
+        });
+    for (auto& x : th) x.join();
+    b2dp_probe_info pi{};
+    EXPECT(b2dp_probe_describe(c, n - 1, &pi) == B2DP_OK && pi.via_helper == 1 && pi.usable == 1);
+    EXPECT(bad.load() == 0);
+    b2dp_close(c);
+    printf("helpers ok: %d units, %d threads, %d passes, %d bad, %d failures\n", n, T, passes.load(), bad.load(), g_fail);
+    return g_fail ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc == 5 && !strcmp(argv[1], "helpers")) return cmd_helpers(argv);
     if (argc >= 4 && !strcmp(argv[1], "sweep")) return cmd_sweep(argc, argv);
     if (argc == 5 && !strcmp(argv[1], "threads")) return cmd_threads(argv);
     fprintf(stderr, "usage: abi_stress sweep <scratch> <sysroot>... | threads <sysroot> <T> <iters>\n");

@@ -12,14 +12,15 @@ public:
     Nvml nvml;
     std::unique_ptr<UnitsBackend> units;
     std::string driver_version;
+    std::mutex probe_mu;  // one fan-out at a time, like the product backend
 };
 
 int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err) {
-    if (cfg.probe_mode != 2) { err = "sanitizer build: no in-process cuda backend (probe=off only)"; return B2DP_E_NOGPU; }
+    if (cfg.probe_mode == 0) { err = "sanitizer build: no in-process cuda backend (probe=off / probe=helpers only)"; return B2DP_E_NOGPU; }
     auto be = std::make_unique<CudaBackend>();
     be->cfg = cfg;
     be->nvml.load();
-    int rc = units_open(cfg, be->nvml, false, &be->units, err);
+    int rc = units_open(cfg, be->nvml, cfg.probe_mode == 1, &be->units, err);
     if (rc != B2DP_OK) return rc;
     char buf[96] = {0};
     if (be->nvml.driver_version && be->nvml.driver_version(buf, sizeof buf) == 0) be->driver_version = buf;
@@ -33,7 +34,11 @@ int cuda_enumerate(CudaBackend* be, std::vector<Device>& out, std::string&) {
     return B2DP_OK;
 }
 int cuda_node_health(CudaBackend* be) { return be->units->units.empty() ? 0 : 1; }
-int cuda_probe(CudaBackend*, const b2dp_probe_opts*, std::vector<b2dp_probe_result>&, std::string& err) { err = "probe=off"; return B2DP_E_UNSUPPORTED; }
+int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_probe_result>& out, std::string& err) {
+    std::lock_guard<std::mutex> l(be->probe_mu);
+    if (!be->units->helpers) { err = "probe=off"; return B2DP_E_UNSUPPORTED; }
+    return units_probe(be->units.get(), opts, out, err);
+}
 int cuda_inject_fault(CudaBackend*, int, uint64_t, uint32_t, std::string&) { return B2DP_E_UNSUPPORTED; }
 int cuda_probe_reset(CudaBackend*, int, std::string&) { return B2DP_E_UNSUPPORTED; }
 int cuda_probe_peek(CudaBackend*, int, uint64_t, uint32_t*, uint64_t, std::string&) { return B2DP_E_UNSUPPORTED; }
@@ -65,7 +70,8 @@ void cuda_prearm(CudaBackend*) {}
 int cuda_describe(CudaBackend* be, int device, b2dp_probe_info* o, std::string& err) {
     if (device < 0 || device >= (int)be->units->units.size()) { err = "device index out of range"; return B2DP_E_INVAL; }
     const Unit& u = be->units->units[device];
-    o->total_memory = (uint64_t)u.vram; o->sm_count = (int32_t)u.sms; o->usable = 1;
+    o->total_memory = (uint64_t)u.vram; o->sm_count = (int32_t)u.sms; o->usable = u.broken ? 0 : 1;
+    o->via_helper = be->units->helpers ? 1 : 0; o->slot_bytes = u.slot_bytes; o->gbs_cal = u.gbs_cal; o->gbs_ref = u.gbs_ref;
     copy_str(o->uuid, sizeof o->uuid, u.uuid);
     copy_str(o->name, sizeof o->name, u.name);
     return B2DP_OK;

@@ -211,3 +211,128 @@ def test_helpers_mode_needs_the_helper_binary_and_nvml(pkg, monkeypatch, stub, t
     for bad in ("cuda:probe=sometimes", "cuda:mig=maybe", "cuda:mig_bytes=7"):
         with pytest.raises(pkg._native.B2dpError):
             pkg.Context(bad)
+
+
+# ---- probe=helpers end to end on a MIG node, without a GPU: the parent side of csrc/units_backend.hpp against a
+# protocol-speaking stand-in child (tests/native/fake_probe_helper.cpp) ----------------------------------------------------
+FAKE = os.path.join(BUILD, "fake_probe_helper")
+
+
+@pytest.fixture(scope="module")
+def fake_helper():
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    os.makedirs(BUILD, exist_ok=True)
+    src = os.path.join(HERE, "native", "fake_probe_helper.cpp")
+    if not os.path.exists(FAKE) or os.path.getmtime(src) > os.path.getmtime(FAKE):
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", src, "-o", FAKE], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    return FAKE
+
+
+def _children():
+    me, pids = os.getpid(), []
+    for d in os.listdir("/proc"):
+        if d.isdigit():
+            try:
+                stat = open("/proc/%s/stat" % d).read()
+                if int(stat.rsplit(")", 1)[1].split()[1]) == me and "fake_probe_hel" in stat:
+                    pids.append(int(d))
+            except OSError:
+                pass
+    return sorted(pids)
+
+
+def test_mig_units_probed_through_helper_processes(pkg, monkeypatch, stub, fake_helper, tmp_path):
+    """A MIG node (2 GPUs x 3 instances) with probe=helpers (what mig=auto selects on such a node): one child per MIG
+    instance, started with CUDA_VISIBLE_DEVICES=<MIG UUID>; the fan-out sends to all before waiting on any; each unit
+    follows the seed schedule of its enumeration index and is judged against the host's closed form; ListAndWatch
+    carries per-instance verdicts; a deadline miss is Unhealthy for that unit only and its late answer is discarded; a
+    child that dies is Unhealthy once and restarted; xid=1 attributes a critical Xid to one GPU instance; closing
+    reaps every child."""
+    import time
+    from oracle import probe as oprobe
+    N = pkg._native
+    monkeypatch.setenv("B2DP_NVML_LIBRARY", stub)
+    monkeypatch.setenv("B2DP_NVML_STUB", "gpus=2,mig=3")
+    monkeypatch.setenv("B2DP_PROBE_HELPER", fake_helper)
+    mark = str(tmp_path / "died_once")
+    monkeypatch.setenv("FAKE_HELPER_MARK", mark)
+    monkeypatch.setenv("FAKE_HELPER_DIE_UNIT", "4")
+    monkeypatch.setenv("FAKE_HELPER_DIE_AFTER", "3")
+    monkeypatch.setenv("FAKE_HELPER_SLOW_UNIT", "2")
+    monkeypatch.setenv("FAKE_HELPER_SLOW_MS", "0")
+    sysroot = _sysroot(tmp_path, 2, 3)
+    mig_bytes = 64 << 20
+    with pkg.Context("cuda:sysroot=%s,mig_bytes=%d,xid=1" % (sysroot, mig_bytes)) as ctx:       # mig=auto => helpers
+        ids = sorted(ctx.enumerate())
+        assert ids == ["0000:19:00.0", "0000:29:00.0", "amdgpu_xcp_1", "amdgpu_xcp_10", "amdgpu_xcp_2", "amdgpu_xcp_9"]
+        assert len(_children()) == 6
+        d = ctx.probe_describe(3)                                     # "amdgpu_xcp_10" = GPU 1, third instance
+        assert d["via_helper"] and d["usable"] and d["slot_bytes"] == mig_bytes and d["gbs_ref"] == 900.0
+        assert d["uuid"] == "MIG-00000001-0002-4000-8000-00000000b200" and d["name"] == "FAKE B200 " + d["uuid"]   # the child saw ITS uuid
+        seeds = [oprobe.initial_seed(i) for i in range(6)]
+        for step in range(3):
+            res = ctx.probe_health(timed=False)
+            assert [r.device for r in res] == list(range(6)) and [r.seed for r in res] == seeds
+            for r in res:
+                assert r.err == 0 and r.healthy and r.bytes == 2 * mig_bytes and abs(r.min_gbs_applied - 720.0) < 1e-3
+                assert r.checksum == r.expected_checksum == oprobe.expected_checksum(mig_bytes // 4, r.seed)
+            seeds = [oprobe.next_seed(s) for s in seeds]
+        # unit 4 dies instead of answering its 4th probe: Unhealthy (E_CUDA) for that instance only, restarted next pass
+        res = ctx.probe_health(timed=False)
+        assert [(r.healthy, r.err) for r in res] == [(True, 0)] * 4 + [(False, N.E_CUDA)] + [(True, 0)]
+        wire, st = ctx.list_and_watch("1g_23gb", N.LW_HEARTBEAT)
+        msg = pkg.v1beta1.ListAndWatchResponse.FromString(wire)
+        assert [d_.health for d_ in msg.devices] == ["Healthy"] * 6 and st.n_devices == 6      # the restarted child answers
+        assert len(_children()) == 6 and os.path.exists(mark)
+        # fault on one instance: reported once
+        ctx.probe_inject_fault(1, 777, 1)
+        res = ctx.probe_health(timed=False)
+        assert [r.healthy for r in res] == [True, False, True, True, True, True] and res[1].first_bad_word == 777
+        assert all(r.healthy for r in ctx.probe_health(timed=False))
+        # the 0.8 line, per instance
+        ctx.probe_set_ref(5, 2000.0)
+        res = ctx.probe_health(timed=False)
+        assert [r.healthy for r in res] == [True] * 5 + [False] and res[5].flags & N.RES_SLOW and abs(res[5].min_gbs_applied - 1600.0) < 1e-3
+        ctx.probe_set_ref(5, 0.0)
+        assert all(r.healthy for r in ctx.probe_health(timed=False))
+        # xid=1: a critical Xid is latched on the instance (sticky until reset); an application-level one is not
+        UINT64_MAX = (1 << 64) - 1
+        ctx.probe_inject_fault(2, UINT64_MAX, 31)
+        assert all(r.healthy for r in ctx.probe_health(timed=False))
+        ctx.probe_inject_fault(2, UINT64_MAX, 79)
+        for _ in range(2):
+            res = ctx.probe_health(timed=False)
+            assert [r.healthy for r in res] == [True, True, False, True, True, True] and res[2].flags & N.RES_XID
+        ctx.probe_reset(2)
+        assert all(r.healthy for r in ctx.probe_health(timed=False))
+        # Start() on declared links, allocation prefers instances of one GPU
+        assert ctx.start() == 0
+        got = ctx.preferred_allocation(ids, [], 3)
+        assert len({ctx.enumerate()[i]["devID"] for i in got}) == 1
+    time.sleep(0.2)
+    assert _children() == []
+
+
+def test_helper_deadline_and_stale_answers(pkg, monkeypatch, stub, fake_helper, tmp_path):
+    """health.go:37 gives the exporter RPC a deadline; here a unit that misses `timeout_ms` is Unhealthy with
+    B2DP_E_TIMEOUT while the others' verdicts stand, the caller returns at the deadline, and the late answer is
+    recognised by its sequence number and dropped before the next verdict."""
+    import time
+    N = pkg._native
+    monkeypatch.setenv("B2DP_NVML_LIBRARY", stub)
+    monkeypatch.setenv("B2DP_NVML_STUB", "gpus=1,mig=2")
+    monkeypatch.setenv("B2DP_PROBE_HELPER", fake_helper)
+    monkeypatch.setenv("FAKE_HELPER_SLOW_UNIT", "1")
+    monkeypatch.setenv("FAKE_HELPER_SLOW_MS", "400")
+    with pkg.Context("cuda:sysroot=%s,mig_bytes=%d" % (_sysroot(tmp_path, 1, 2), 1 << 20)) as ctx:
+        t0 = time.perf_counter()
+        res = ctx.probe_health(timed=False, timeout_ms=100, min_gbs=1.0)
+        waited = time.perf_counter() - t0
+        assert [(r.healthy, r.err) for r in res] == [(True, 0), (False, N.E_TIMEOUT)] and waited < 0.35
+        wire, st = ctx.list_and_watch("1g_23gb", N.LW_HEARTBEAT, timeout_ms=100, min_gbs=1.0)
+        assert st.n_unhealthy == 1
+        res = ctx.probe_health(timed=False, timeout_ms=5000, min_gbs=1.0)       # waits out the slow child: both fresh answers
+        assert [(r.healthy, r.err) for r in res] == [(True, 0), (True, 0)]
+        assert res[1].seed != res[0].seed

@@ -141,6 +141,26 @@ def test_mig_enumeration_under_sanitizers(bins, which, tmp_path):
     assert "Sanitizer" not in r.stderr and "runtime error" not in r.stderr
 
 
+@pytest.mark.parametrize("which", ["asan", "tsan"])
+def test_helper_fan_out_under_sanitizers(bins, which, tmp_path):
+    """The parent side of probe=helpers (spawn, socketpair protocol, fan-out, reaping; csrc/units_backend.hpp) on a
+    2 x 3-instance MIG node with protocol-speaking stand-in children: 3 threads x 12 passes on one context."""
+    import test_mig_enumeration as tm
+    for out, src, extra in ((tm.STUB, "nvml_stub.cpp", ["-shared", "-fPIC", "-fvisibility=hidden"]), (tm.FAKE, "fake_probe_helper.cpp", [])):
+        os.makedirs(tm.BUILD, exist_ok=True)
+        srcp = os.path.join(HERE, "native", src)
+        if not os.path.exists(out) or os.path.getmtime(srcp) > os.path.getmtime(out):
+            r = subprocess.run(["g++", "-std=c++17", "-O1"] + extra + [srcp, "-o", out], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+    env = _env()
+    env.update(B2DP_NVML_LIBRARY=tm.STUB, B2DP_NVML_STUB="gpus=2,mig=3", B2DP_PROBE_HELPER=tm.FAKE)
+    uri = "cuda:probe=helpers,mig_bytes=1048576,sysroot=" + tm._sysroot(tmp_path, 2, 3)
+    r = subprocess.run([bins[which], "helpers", uri, "3", "12"], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-6000:])
+    assert "helpers ok: 6 units, 3 threads, 36 passes, 0 bad, 0 failures" in r.stdout
+    assert "Sanitizer" not in r.stderr and "runtime error" not in r.stderr
+
+
 @pytest.mark.parametrize("san", ["address,undefined", "thread"])
 def test_native_daemon_under_sanitizers(san, tmp_path):
     """b200dp_plugind (csrc/host: HTTP/2 + HPACK + gRPC, the watch threads, the signal loop) rebuilt under
