@@ -821,3 +821,41 @@ def subprocess_pids_of_helpers():
         except OSError:
             pass
     return sorted(pids)
+
+
+def test_probe_off_enumerates_real_gpus_through_nvml(P):
+    """probe=off on real hardware: the same device table as the in-process backend, built from NVML alone (no CUDA
+    context, no HBM ring -- the free memory of the GPUs does not move), labels from NVML equal to the in-process
+    backend's CUDA/NVML answers, and the native daemon's labeller mode on top of it."""
+    import json
+    import subprocess
+    import torch
+    with P.Context("cuda:bytes=%d,calib=0" % MiB) as direct:
+        table = direct.enumerate()
+        gens = ["driver-version", "device-id", "product-name", "simd-count", "cu-count", "family", "firmware",
+                "compute-memory-partition", "compute-partitioning-supported", "memory-partitioning-supported"]
+        want = direct.generate_labels(gens)
+        want_vram = direct.generate_labels(["vram"])
+    free0 = [torch.cuda.mem_get_info(i)[0] for i in range(torch.cuda.device_count())]
+    with P.Context("cuda:probe=off") as ctx:
+        assert ctx.enumerate() == table
+        assert [torch.cuda.mem_get_info(i)[0] for i in range(torch.cuda.device_count())] == free0      # nothing allocated
+        assert ctx.generate_labels(gens) == want
+        got_vram = ctx.generate_labels(["vram"])
+        # NVML's total (the whole HBM) vs CUDA's totalGlobalMem (minus the driver's reservation) may round to
+        # neighbouring GiB values; both are B200-sized
+        assert set(got_vram) == set(k.replace(want_vram["amd.com/gpu.vram"], got_vram["amd.com/gpu.vram"]) for k in want_vram)
+        assert 170 <= int(got_vram["amd.com/gpu.vram"][:-1]) <= 192
+        d = ctx.probe_describe(0)
+        assert d["uuid"].startswith("GPU-") and d["sm_count"] == 148 and not d["via_helper"]
+        with pytest.raises(P._native.B2dpError) as ei:
+            ctx.probe_health()
+        assert ei.value.code == P._native.E_UNSUPPORTED
+        ids = sorted(table)
+        resp = P.v1beta1.ContainerAllocateResponse.FromString(ctx.allocate_response(ids[:1]))
+        assert dict(resp.envs)["NVIDIA_VISIBLE_DEVICES"] == d["uuid"]
+        assert [x.host_path for x in resp.devices][-1] == "/dev/nvidia%d" % table[ids[0]]["card"]
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "k8s-device-plugin_b200", "b200dp_plugind")
+    r = subprocess.run([exe, "-labels=" + ",".join(gens), "-backend=cuda:"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout) == want
