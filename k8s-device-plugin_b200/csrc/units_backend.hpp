@@ -65,6 +65,9 @@ struct Unit {
     uint64_t slot_bytes = 0;
     float gbs_cal = 0.f, gbs_ref = 0.f;
     std::string helper_uri;
+    bool starting = false;        // a (re)started child has been sent HELLO and has not answered yet
+    uint64_t hello_seq = 0;
+    std::chrono::steady_clock::time_point start_t{};
 };
 
 struct UnitsBackend {
@@ -123,12 +126,11 @@ static inline int units_recv(Unit& u, void* p, size_t n, std::chrono::steady_clo
     char* c = static_cast<char*>(p);
     while (n) {
         const auto now = std::chrono::steady_clock::now();
-        if (now >= deadline) return 0;
         struct pollfd pf{u.fd, POLLIN, 0};
-        const int ms = (int)std::chrono::duration_cast<std::chrono::milliseconds>(deadline - now).count();
-        const int pr = poll(&pf, 1, ms > 0 ? ms : 1);
+        const long long left = std::chrono::duration_cast<std::chrono::milliseconds>(deadline - now).count();
+        const int pr = poll(&pf, 1, left > 0 ? (int)left : 0);  // a deadline already reached still gets one look
         if (pr < 0) { if (errno == EINTR) continue; return -1; }
-        if (pr == 0) continue;
+        if (pr == 0) { if (std::chrono::steady_clock::now() >= deadline) return 0; continue; }
         const ssize_t r = recv(u.fd, c, n, 0);
         if (r == 0) return -1;
         if (r < 0) { if (errno == EINTR || errno == EAGAIN) continue; return -1; }
@@ -194,25 +196,62 @@ static inline bool units_spawn(UnitsBackend* ub, Unit& u, std::string& err) {
     return true;
 }
 
-// Start (or restart) u's helper and learn what it holds.
-static inline bool units_start_helper(UnitsBackend* ub, Unit& u, std::string& err) {
+// (Re)start u's helper without waiting for it: spawn, send HELLO.  A fresh CUDA process needs seconds to come up;
+// a heartbeat must not stall on that, so the answer is collected later (units_finish_start).
+static inline bool units_begin_start(UnitsBackend* ub, Unit& u, std::string& err) {
     units_kill(u);
+    u.starting = false;
     if (!units_spawn(ub, u, err)) return false;
     HelperReq q{};
+    q.magic = kHelperMagic;
     q.op = HOP_HELLO;
+    q.seq = u.hello_seq = ++u.seq;
+    if (!units_send(u, q)) { err = "probe helper exited at start"; units_kill(u); return false; }
+    u.starting = true;
+    u.start_t = std::chrono::steady_clock::now();
+    return true;
+}
+
+// Has the child answered HELLO?  1 ready (u describes what it holds), 0 not yet, -1 failed (child dropped, err says why).
+static inline int units_finish_start(Unit& u, int wait_ms, std::string& err) {
     HelperRsp r{};
-    const int rc = units_call(u, q, &r, 120000);  // the first CUDA initialisation of a fresh process can take a while
-    if (rc != B2DP_OK || r.rc != B2DP_OK) {
-        err = rc != B2DP_OK ? "probe helper did not answer" : std::string("probe helper: ") + r.text;
-        units_kill(u);
-        return false;
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(wait_ms);
+    for (;;) {
+        const int rc = units_recv(u, &r, sizeof r, deadline);
+        if (rc == 0) {
+            if (std::chrono::steady_clock::now() - u.start_t < std::chrono::seconds(120)) return 0;
+            err = "probe helper did not answer within 120 s";
+            units_kill(u); u.starting = false;
+            return -1;
+        }
+        if (rc < 0 || r.magic != kHelperMagic) { err = "probe helper exited while starting"; units_kill(u); u.starting = false; return -1; }
+        if (r.seq == u.hello_seq) break;
     }
+    u.starting = false;
+    if (r.rc != B2DP_OK) { err = std::string("probe helper: ") + r.text; units_kill(u); return -1; }
     if (r.text[0]) u.name = r.text;
     if (r.extra[0]) u.sms = (int64_t)r.extra[0];
     if (r.extra[1]) u.vram = (int64_t)r.extra[1];
     u.slot_bytes = r.extra[2];
     memcpy(&u.gbs_cal, &r.extra[3], sizeof(float));
-    return true;
+    if (u.gbs_ref > 0) {  // a restarted child inherits the ceiling its predecessor was judged against
+        HelperReq q{};
+        q.op = HOP_SETREF;
+        memcpy(&q.a, &u.gbs_ref, sizeof(float));
+        HelperRsp r2{};
+        units_call(u, q, &r2, 2000);
+    }
+    return 1;
+}
+
+// Start u's helper and wait for it (context open).
+static inline bool units_start_helper(UnitsBackend* ub, Unit& u, std::string& err) {
+    if (!units_begin_start(ub, u, err)) return false;
+    for (;;) {
+        const int st = units_finish_start(u, 1000, err);
+        if (st > 0) return true;
+        if (st < 0) return false;
+    }
 }
 
 // ---- open -------------------------------------------------------------------------------------------------------------
@@ -430,10 +469,20 @@ static inline int units_probe(UnitsBackend* ub, const b2dp_probe_opts* opts, std
         out[i].device = (int)i;
         out[i].first_bad_word = ~0ull;
         if (u.broken) {
-            std::string e2;  // a helper that died is restarted on the next heartbeat
-            if (u.helper_uri.empty() || u.broken_reason.find("injected") != std::string::npos || !units_start_helper(ub, u, e2)) {
-                out[i].err = B2DP_E_CUDA; state[i] = 2; err = u.broken_reason + " on " + u.dev.id; continue;
+            // A helper that died is restarted by the next heartbeat -- without stalling it: the child is spawned and
+            // greeted, and whichever heartbeat finds its answer (this one, if it comes within 250 ms; a fresh CUDA
+            // process takes seconds) puts the unit back in service.  Until then the unit is reported Unhealthy.
+            std::string e2;
+            bool ready = false;
+            if (!u.helper_uri.empty() && u.broken_reason.find("injected") == std::string::npos) {
+                if (u.starting || units_begin_start(ub, u, e2)) {
+                    const int st = units_finish_start(u, (int)std::min<uint32_t>(timeout_ms, 250), e2);
+                    ready = st > 0;
+                    if (st == 0) e2 = "probe helper is starting";
+                }
+                if (!ready && !e2.empty()) u.broken_reason = e2;
             }
+            if (!ready) { out[i].err = B2DP_E_CUDA; state[i] = 2; err = u.broken_reason + " on " + u.dev.id; continue; }
             u.broken = false;
         }
         HelperReq q{};

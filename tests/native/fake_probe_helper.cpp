@@ -7,6 +7,7 @@
 //   FAKE_HELPER_SLOW_UNIT=<i> FAKE_HELPER_SLOW_MS=<ms>   unit i answers every PROBE after sleeping ms
 //   FAKE_HELPER_DIE_UNIT=<i>  FAKE_HELPER_DIE_AFTER=<n>  unit i exits instead of answering its (n+1)-th PROBE -- once: a
 //                                                        restarted child (FAKE_HELPER_MARK file exists) lives on
+//   FAKE_HELPER_RESTART_HELLO_MS=<ms>                    a restarted child takes this long to answer HELLO
 #include <unistd.h>
 
 #include <cerrno>
@@ -57,6 +58,7 @@ int main(int argc, char** argv) {
         r.seq = q.seq;
         switch (q.op) {
             case HOP_HELLO:
+                if (restarted) usleep(1000u * (unsigned)env_int("FAKE_HELPER_RESTART_HELLO_MS", 0));  // a slow-starting (CUDA-like) restart
                 snprintf(r.text, sizeof r.text, "FAKE B200 %s", vis ? vis : "?");
                 r.extra[0] = 18; r.extra[1] = 23ull << 30; r.extra[2] = bytes;
                 memcpy(&r.extra[3], &gbs_ref, sizeof gbs_ref);

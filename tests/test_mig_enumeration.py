@@ -336,3 +336,37 @@ def test_helper_deadline_and_stale_answers(pkg, monkeypatch, stub, fake_helper, 
         res = ctx.probe_health(timed=False, timeout_ms=5000, min_gbs=1.0)       # waits out the slow child: both fresh answers
         assert [(r.healthy, r.err) for r in res] == [(True, 0), (True, 0)]
         assert res[1].seed != res[0].seed
+
+
+def test_helper_restart_does_not_stall_the_heartbeat(pkg, monkeypatch, stub, fake_helper, tmp_path):
+    """A fresh CUDA process needs seconds to come up.  The heartbeat that finds a dead helper, and the ones that follow
+    while its replacement starts, return promptly with that unit Unhealthy (the others' verdicts stand); the first
+    heartbeat after the replacement answered HELLO puts the unit back in service, on the ceiling its predecessor had."""
+    import time
+    N = pkg._native
+    monkeypatch.setenv("B2DP_NVML_LIBRARY", stub)
+    monkeypatch.setenv("B2DP_NVML_STUB", "gpus=1,mig=3")
+    monkeypatch.setenv("B2DP_PROBE_HELPER", fake_helper)
+    monkeypatch.setenv("FAKE_HELPER_MARK", str(tmp_path / "died"))
+    monkeypatch.setenv("FAKE_HELPER_DIE_UNIT", "1")
+    monkeypatch.setenv("FAKE_HELPER_DIE_AFTER", "1")
+    monkeypatch.setenv("FAKE_HELPER_RESTART_HELLO_MS", "900")
+    with pkg.Context("cuda:sysroot=%s,mig_bytes=%d" % (_sysroot(tmp_path, 1, 3), 1 << 20)) as ctx:
+        ctx.probe_set_ref(-1, 1000.0)
+        assert all(r.healthy for r in ctx.probe_health(timed=False))
+        res = ctx.probe_health(timed=False)                           # unit 1 dies instead of answering
+        assert [(r.healthy, r.err) for r in res] == [(True, 0), (False, N.E_CUDA), (True, 0)]
+        seen_starting = 0
+        t_end = time.time() + 10
+        while time.time() < t_end:
+            t0 = time.perf_counter()
+            res = ctx.probe_health(timed=False)
+            assert time.perf_counter() - t0 < 0.6                     # never the 0.9 s the replacement takes
+            assert res[0].healthy and res[2].healthy
+            if res[1].err == 0:
+                break
+            assert res[1].err == N.E_CUDA and not ctx.probe_describe(1)["usable"]
+            seen_starting += 1
+            time.sleep(0.1)
+        assert res[1].healthy and seen_starting >= 1 and abs(res[1].gbs_ref - 1000.0) < 1e-3     # the inherited ceiling
+        assert ctx.probe_describe(1)["usable"]
