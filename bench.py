@@ -617,6 +617,8 @@ def main():
     else:
         flag.wait()
     barrier()
+    if rank == 0:
+        flag.clear()
 
     clocks = sampler.stop(windows) if sampler else None
     if rank != 0:
