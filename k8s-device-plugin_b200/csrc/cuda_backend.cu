@@ -805,7 +805,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     // GB/s floor: an absolute one if the call or the context names it (min_gbs), else min_frac (default 0.8,
     // BASELINE.json's ">= 80 % of HBM peak") of the device's calibrated ceiling
     const float abs_floor = opts && opts->min_gbs > 0 ? opts->min_gbs : be->cfg.min_gbs;
-    const int grid = opts ? (int)opts->grid_ctas : 0;
+    const int grid = opts ? (int)std::min<uint32_t>(opts->grid_ctas, 1u << 16) : 0;  // diagnostic hook, bounded
     const size_t n = be->gpus.size();
     std::vector<std::shared_ptr<ProbeJobResult>> res(n);
     std::vector<std::shared_ptr<Completion>> cs(n);
