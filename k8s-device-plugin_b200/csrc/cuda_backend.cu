@@ -1170,6 +1170,7 @@ int cuda_set_ref(CudaBackend* be, int device, float gbs_ref, std::string& err) {
 int cuda_describe(CudaBackend* be, int device, b2dp_probe_info* o, std::string& err) {
     if (device < 0 || device >= cuda_device_count(be)) { err = "device index out of range"; return B2DP_E_INVAL; }
     if (be->units) {
+        std::lock_guard<std::mutex> pl(be->probe_mu);  // a fan-out may be restarting this unit's helper
         const Unit& u = be->units->units[device];
         o->slot_bytes = u.slot_bytes; o->total_memory = (uint64_t)u.vram; o->sm_count = (int32_t)u.sms; o->slots = be->cfg.slots;
         o->gbs_cal = u.gbs_cal; o->gbs_ref = u.gbs_ref; o->usable = u.broken ? 0 : 1; o->via_helper = be->units->helpers ? 1 : 0;
