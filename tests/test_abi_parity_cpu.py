@@ -529,3 +529,38 @@ def test_synthetic_backend_equals_the_written_tree(P, tmp_path, n, mig):
     for bad in ("synthetic:0", "synthetic:8,mig=9", "synthetic:8,frob=1", "synthetic:abc"):
         with pytest.raises(P._native.B2dpError):
             P.Context(bad)
+
+
+def test_struct_layouts_match_the_c_header(P, tmp_path):
+    """Struct layouts are part of the ABI: sizeof/offsetof as a C compiler sees include/b200dp.h == the ctypes mirror
+    (a cgo or ctypes host built against another layout would read garbage, so B2DP_ABI_VERSION moves with them)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    N = P._native
+    pairs = [("b2dp_device", N.Device), ("b2dp_kv_count", N.KvCount), ("b2dp_label", N.Label), ("b2dp_devspec", N.DevSpec),
+             ("b2dp_pair_weight", N.PairWeight), ("b2dp_link", N.Link), ("b2dp_fw_entry", N.FwEntry),
+             ("b2dp_probe_opts", N.ProbeOpts), ("b2dp_probe_result", N.ProbeResult), ("b2dp_cycle_opts", N.CycleOpts),
+             ("b2dp_cycle_stats", N.CycleStats), ("b2dp_p2p_opts", N.P2pOpts), ("b2dp_probe_info", N.ProbeInfo)]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200dp.h"', 'int main(void) {']
+    for cname, ct in pairs:
+        src.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            src.append('printf(" %s=%%zu", offsetof(%s, %s));' % (fname, cname, fname))
+        src.append('printf("\\n");')
+    src += ['return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    r = subprocess.run(["gcc", "-std=c11", "-I", os.path.join(REPO, "include"), str(c), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True).stdout.splitlines()
+    assert len(out) == len(pairs)
+    for line, (cname, ct) in zip(out, pairs):
+        parts = line.split()
+        assert parts[0] == cname and int(parts[1]) == ctypes.sizeof(ct), (cname, parts[1], ctypes.sizeof(ct))
+        for tok, (fname, _) in zip(parts[2:], ct._fields_):
+            k, v = tok.split("=")
+            assert k == fname and int(v) == getattr(ct, fname).offset, (cname, fname, v, getattr(ct, fname).offset)
+    assert ctypes.sizeof(N.ProbeResult) == 88 and ctypes.sizeof(N.CycleStats) == 64
