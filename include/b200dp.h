@@ -69,6 +69,13 @@ enum {
     B2DP_E_ALLOC_SUBSET_AVAIL = -29   /* "subset size is more than available devices" */
 };
 
+/* Diagnostics.  The library never prints (the reference logs through glog, e.g. the warnings of amdgpu.go:171-195 and
+ * the health transitions around plugin.go:304-320); a host that wants those lines installs ONE process-wide callback
+ * and routes them to its logger.  level: 0 info, 1 warning, 2 error.  `msg` is valid during the call; the callback may
+ * run on any library thread and must not call back into the library.  NULL removes it. */
+typedef void (*b2dp_log_cb)(void *user, int level, const char *msg);
+B2DP_API void b2dp_set_log_callback(b2dp_log_cb cb, void *user);
+
 /* Static message for a code; allocator codes return the reference's error strings. */
 B2DP_API const char *b2dp_strerror(int code);
 B2DP_API int b2dp_abi_version(void);

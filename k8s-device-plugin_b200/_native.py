@@ -114,6 +114,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 WatchCb = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(CycleStats))
+LogCb = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p)
 
 _P = C.POINTER
 _vp, _cp, _i, _ip = C.c_void_p, C.c_char_p, C.c_int, _P(C.c_int)
@@ -122,6 +123,7 @@ _strs = _P(C.c_char_p)
 
 # name -> (restype, argtypes); every function b200dp.h declares
 SIGNATURES = {
+    "b2dp_set_log_callback": (None, [LogCb, _vp]),
     "b2dp_strerror": (C.c_char_p, [_i]),
     "b2dp_abi_version": (_i, []),
     "b2dp_parse_topology_property": (_i, [_cp, _cp, _P(C.c_int64)]),
@@ -225,3 +227,18 @@ def grow_call(make_array, call):
             cap = max(n.value, cap * 2)
             continue
         return rc, arr, n.value
+
+
+_log_keepalive = None
+
+
+def set_log_callback(fn):
+    """Route the library's diagnostics to `fn(level, message)` (level 0 info / 1 warning / 2 error); None removes it."""
+    global _log_keepalive
+    if fn is None:
+        lib.b2dp_set_log_callback(C.cast(None, LogCb), None)
+        _log_keepalive = None
+        return
+    cb = LogCb(lambda _user, level, msg: fn(level, msg.decode("utf-8", "replace")))
+    lib.b2dp_set_log_callback(cb, None)
+    _log_keepalive = cb

@@ -3,8 +3,10 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
+#include <cstdarg>
 #include <climits>
 #include <condition_variable>
 #include <thread>
@@ -55,6 +57,33 @@ static int enumerate_ctx(b2dp_ctx* c, std::vector<Device>& devs) {
     int rc = c->kind == b2dp_ctx::KFD ? kfd_enumerate(c->sysroot, devs, err) : cuda_enumerate(c->cuda, devs, err);
     if (rc != B2DP_OK) t_last_error = err;
     return rc;
+}
+
+// ---- diagnostics -------------------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_log_mu;
+b2dp_log_cb g_log_cb = nullptr;
+void* g_log_user = nullptr;
+std::atomic<bool> g_log_on{false};
+}  // namespace
+namespace b2dp {
+bool log_enabled() { return g_log_on.load(std::memory_order_relaxed); }
+void logf(int level, const char* fmt, ...) {
+    if (!log_enabled()) return;
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> l(g_log_mu);  // serialises callbacks; the callback must not re-enter the library
+    if (g_log_cb) g_log_cb(g_log_user, level, buf);
+}
+}  // namespace b2dp
+extern "C" void b2dp_set_log_callback(b2dp_log_cb cb, void* user) {
+    std::lock_guard<std::mutex> l(g_log_mu);
+    g_log_cb = cb;
+    g_log_user = user;
+    g_log_on.store(cb != nullptr);
 }
 
 extern "C" const char* b2dp_strerror(int code) {
@@ -478,6 +507,11 @@ extern "C" int b2dp_list_and_watch(b2dp_ctx* c, const char* resource, const b2dp
             st.probe_frac_min = 1e30f;
             for (auto& r : res) {
                 if (r.device >= 0 && r.device < (int)devs.size()) hmap[devs[r.device].id] = r.healthy;
+                if (!r.healthy && log_enabled() && r.device >= 0 && r.device < (int)devs.size())  // why the bit flipped
+                    logf(1, "%s Unhealthy: err=%d (%s) mismatches=%llu first_bad_word=%llu checksum_%s rate=%.0f GB/s floor=%.0f (%.3f of ceiling %.0f) flags=0x%x",
+                         devs[r.device].id.c_str(), r.err, b2dp_strerror(r.err), (unsigned long long)r.mismatches,
+                         (unsigned long long)r.first_bad_word, r.checksum == r.expected_checksum ? "ok" : "BAD", r.gbs, r.min_gbs_applied, r.frac,
+                         r.gbs_ref, r.flags);
                 st.probe_bytes += r.bytes;
                 st.probe_gbs_sum += r.gbs;
                 if (r.gbs < st.probe_gbs_min) st.probe_gbs_min = r.gbs;

@@ -370,6 +370,12 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
     if (mode != 0) {
         int rc = units_open(cfg, be->nvml, mode == 1, &be->units, err);
         if (rc != B2DP_OK) return rc;
+        {
+            int n_mig = 0;
+            for (auto& u : be->units->units) n_mig += u.mig_slot >= 0;
+            logf(0, "NVML enumeration: %zu unit(s), %d MIG instance(s), probe=%s%s", be->units->units.size(), n_mig, mode == 1 ? "helpers" : "off",
+                 cfg.probe_mode == 0 ? " (forced by MIG: CUDA shows a process one compute instance)" : "");
+        }
         if (be->nvml.driver_version) {
             char buf[96] = {0};
             if (be->nvml.driver_version(buf, sizeof buf) == 0) be->driver_version = buf;
@@ -597,6 +603,7 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
         g->broken = true;
         g->broken_reason = forced ? "setup failure injected (break=)" : cuda_err(where[i], errs[i]);
         g->last_healthy = 0;
+        logf(2, "%s could not be set up and will be reported Unhealthy: %s", g->dev.id.c_str(), g->broken_reason.c_str());
         err = g->broken_reason + " on " + g->dev.id;
         ++n_broken;
     }
@@ -615,6 +622,9 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
             for (auto& o : be->gpus)
                 if (!o->broken && o->name == g->name && o->n_vec == g->n_vec) ref = std::max(ref, o->gbs_cal);
         g->gbs_ref.store(ref);
+        logf(0, "%s %s ring %d x %llu MiB%s, calibrated %.0f GB/s, ceiling %.0f GB/s, floor %.0f GB/s", g->dev.id.c_str(), g->name.c_str(),
+             (int)g->buf.size(), (unsigned long long)(g->n_vec * 16 >> 20), g->small_ring ? " (shrunk: HBM was short)" : "", g->gbs_cal, ref,
+             cfg.min_gbs > 0 ? cfg.min_gbs : cfg.min_frac * ref);
     }
     // launchers=2: split the GPUs by NUMA node (GPU 0's node stays with the caller; one NUMA node: split in halves)
     for (size_t i = 0; i < be->gpus.size(); ++i) be->caller_idx.push_back(i);
@@ -783,7 +793,7 @@ static void xid_listener(CudaBackend* be) {
                 be->unit_xid[i]->compare_exchange_strong(none, d.data ? d.data : 999);
                 hit = true;
             }
-        if (hit) be->fire_health_event();
+        if (hit) { logf(2, "critical Xid %llu reported by NVML: device(s) latched Unhealthy", d.data); be->fire_health_event(); }
     }
 }
 

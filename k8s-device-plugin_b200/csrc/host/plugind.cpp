@@ -501,6 +501,8 @@ int main(int argc, char** argv) {
     pthread_sigmask(SIG_BLOCK, &sigs, nullptr);
     signal(SIGPIPE, SIG_IGN);
 
+    // the library's diagnostics (why a device flipped Unhealthy, helper restarts, Xids, calibration) go to stderr like glog's
+    b2dp_set_log_callback([](void*, int level, const char* msg) { fprintf(stderr, "%c libb200dp: %s\n", level >= 2 ? 'E' : level == 1 ? 'W' : 'I', msg); }, nullptr);
     b2dp_ctx* ctx = nullptr;
     int rc = b2dp_open(fl.backend.c_str(), &ctx);
     if (rc != B2DP_OK) { logf("open %s: %s (%s)", fl.backend.c_str(), b2dp_strerror(rc), b2dp_last_error(nullptr)); return 1; }

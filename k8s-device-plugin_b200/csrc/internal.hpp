@@ -13,6 +13,10 @@
 
 namespace b2dp {
 
+// ---- diagnostics (ctx.cpp): routed to the host's b2dp_set_log_callback, dropped if there is none ----------------
+void logf(int level, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+bool log_enabled();
+
 struct Device {
     std::string id, dev_id, compute, memory;
     int card = 0, render_d = 128, node_id = 0, numa = -1;

@@ -483,6 +483,7 @@ static inline int units_probe(UnitsBackend* ub, const b2dp_probe_opts* opts, std
                 if (!ready && !e2.empty()) u.broken_reason = e2;
             }
             if (!ready) { out[i].err = B2DP_E_CUDA; state[i] = 2; err = u.broken_reason + " on " + u.dev.id; continue; }
+            logf(0, "%s: probe helper (pid %d) is back in service", u.dev.id.c_str(), (int)u.pid);
             u.broken = false;
         }
         HelperReq q{};
@@ -500,6 +501,7 @@ static inline int units_probe(UnitsBackend* ub, const b2dp_probe_opts* opts, std
             const int rc = units_recv(u, &r, sizeof r, deadline);
             if (rc == 0) { u.stale++; out[i].err = B2DP_E_TIMEOUT; state[i] = 2; break; }
             if (rc < 0 || r.magic != kHelperMagic) {
+                logf(2, "%s: probe helper (pid %d) exited; reported Unhealthy, a replacement starts with the next heartbeat", u.dev.id.c_str(), (int)u.pid);
                 u.broken = true; u.broken_reason = "probe helper exited"; units_kill(u);
                 out[i].err = B2DP_E_CUDA; state[i] = 2; err = u.broken_reason + " on " + u.dev.id; break;
             }

@@ -351,7 +351,19 @@ def test_helper_restart_does_not_stall_the_heartbeat(pkg, monkeypatch, stub, fak
     monkeypatch.setenv("FAKE_HELPER_DIE_UNIT", "1")
     monkeypatch.setenv("FAKE_HELPER_DIE_AFTER", "1")
     monkeypatch.setenv("FAKE_HELPER_RESTART_HELLO_MS", "900")
+    logs = []
+    N.set_log_callback(lambda level, msg: logs.append((level, msg)))       # what glog would have shown (b2dp_set_log_callback)
+    try:
+        _restart_scenario(pkg, tmp_path, logs)
+    finally:
+        N.set_log_callback(None)
+
+
+def _restart_scenario(pkg, tmp_path, logs):
+    import time
+    N = pkg._native
     with pkg.Context("cuda:sysroot=%s,mig_bytes=%d" % (_sysroot(tmp_path, 1, 3), 1 << 20)) as ctx:
+        assert any(lv == 0 and "3 unit(s), 3 MIG instance(s), probe=helpers (forced by MIG" in m for lv, m in logs), logs
         ctx.probe_set_ref(-1, 1000.0)
         assert all(r.healthy for r in ctx.probe_health(timed=False))
         res = ctx.probe_health(timed=False)                           # unit 1 dies instead of answering
@@ -370,3 +382,10 @@ def test_helper_restart_does_not_stall_the_heartbeat(pkg, monkeypatch, stub, fak
             time.sleep(0.1)
         assert res[1].healthy and seen_starting >= 1 and abs(res[1].gbs_ref - 1000.0) < 1e-3     # the inherited ceiling
         assert ctx.probe_describe(1)["usable"]
+        assert any(lv == 2 and "amdgpu_xcp_1: probe helper" in m and "exited" in m for lv, m in logs), logs
+        assert any(lv == 0 and "amdgpu_xcp_1: probe helper" in m and "back in service" in m for lv, m in logs), logs
+        # the reason a device flipped is logged with the heartbeat that flips it
+        ctx.probe_inject_fault(2, 4242, 1)
+        wire, st = ctx.list_and_watch("1g_23gb", N.LW_HEARTBEAT)
+        assert st.n_unhealthy == 1
+        assert any(lv == 1 and m.startswith("amdgpu_xcp_2 Unhealthy:") and "mismatches=1 first_bad_word=4242 checksum_BAD" in m for lv, m in logs), logs
