@@ -177,6 +177,7 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     A GPU whose own setup fails (or that break=<i>+<j>, a test hook, names by enumeration index)
  *                     stays in the device list and is reported Unhealthy with B2DP_E_CUDA on every pass; the open
  *                     only fails when no GPU could be set up.
+ *   "nvml:[k=v,...]"  shorthand for "cuda:probe=off,..." (NVML enumeration only).
  * B2DP_E_NODRIVER (kfd: driver dir absent) | B2DP_E_NOGPU | B2DP_E_CUDA | B2DP_E_INVAL. */
 B2DP_API int b2dp_open(const char *backend_uri, b2dp_ctx **out);
 B2DP_API void b2dp_close(b2dp_ctx *ctx);
@@ -255,7 +256,8 @@ typedef struct b2dp_probe_result {
 #define B2DP_RES_XID 0x8u          /* xid=1: a critical Xid event was delivered for this device since open (or the
                                       last b2dp_probe_reset) => Unhealthy, sticky */
 
-/* Launch the probe on every GPU of the context concurrently (one worker thread + stream per
+/* Replaces the exporter round trip getGPUHealth (exporter/health.go:42-82) and the evidence behind simpleHealthCheck
+ * (plugin.go:161-206): launch the probe on every GPU of the context concurrently (one worker thread + stream per
  * GPU; all launched before any is waited on) and collect one result per device. */
 B2DP_API int b2dp_probe_health(b2dp_ctx *ctx, const b2dp_probe_opts *opts, b2dp_probe_result *out, int cap, int *n);
 

@@ -191,6 +191,7 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         *out = c;
         return B2DP_OK;
     }
+    if (u.compare(0, 5, "nvml:") == 0) return b2dp_open(("cuda:probe=off" + (u.size() > 5 ? "," + u.substr(5) : std::string())).c_str(), out);  // SURVEY 8(b)'s name for it
     if (u.compare(0, 5, "cuda:") == 0) {
         std::map<std::string, std::string> kv;
         if (!parse_kv(u.substr(5), kv)) return fail(B2DP_E_INVAL, "bad cuda: uri");

@@ -192,6 +192,8 @@ def test_whole_gpus_through_nvml_and_mixed_node(pkg, monkeypatch, stub, tmp_path
         assert "amd.com/gpu.compute-memory-partition" not in labels             # heterogeneous: main.go:355-368 emits nothing
         assert labels["beta.amd.com/gpu.cu-count.18"] == "6" and labels["beta.amd.com/gpu.cu-count.148"] == "2"
         assert labels["beta.amd.com/gpu.vram.23G"] == "6"
+    with pkg.Context("nvml:sysroot=%s" % _sysroot(tmp_path, 4, 3)) as ctx:       # the short name for cuda:probe=off
+        assert len(ctx.enumerate()) == 8
     # mig=off lists the physical GPUs even when MIG mode is enabled
     with _open(pkg, monkeypatch, stub, tmp_path, 2, 3, ",mig=off") as ctx:
         assert sorted(ctx.enumerate()) == ["0000:19:00.0", "0000:29:00.0"]
