@@ -391,3 +391,39 @@ def _restart_scenario(pkg, tmp_path, logs):
         wire, st = ctx.list_and_watch("1g_23gb", N.LW_HEARTBEAT)
         assert st.n_unhealthy == 1
         assert any(lv == 1 and m.startswith("amdgpu_xcp_2 Unhealthy:") and "mismatches=1 first_bad_word=4242 checksum_BAD" in m for lv, m in logs), logs
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_mig_layouts_equal_the_oracle_on_the_export(pkg, monkeypatch, stub, tmp_path, seed):
+    """Random nodes (1-8 GPUs, 1-7 instances, any subset of GPUs partitioned): the table built from NVML, the pair weights
+    and the preferred allocations equal what the reference algorithm computes on the exported tree."""
+    import random
+    rnd = random.Random(1000 + seed)
+    gpus, mig = rnd.randint(1, 8), rnd.randint(1, 7)
+    mask = rnd.randint(0, (1 << gpus) - 1)
+    with _open(pkg, monkeypatch, stub, tmp_path, gpus, mig, migmask=mask) as ctx:
+        devs = ctx.enumerate()
+        n_part = bin(mask).count("1")
+        assert len(devs) == n_part * mig + (gpus - n_part)
+        root = str(tmp_path / "export")
+        ctx.export_kfd_tree(root)
+        assert devs == oamd.GetAMDGPUs(root)
+        ids = sorted(devs)
+        rc = ctx.start()
+        opol = oalloc.BestEffortPolicy()
+        oerr = opol.Init(oplug.getDevices(root), root + "/sys/class/kfd/kfd/topology/nodes")
+        if len(ids) < 2:
+            assert rc != 0 and oerr is not None
+            return
+        assert rc == 0 and oerr is None and ctx.pair_weights() == opol.p2pWeights
+        sub = ids if len(ids) <= 12 else rnd.sample(ids, 12)         # the oracle's search is factorial in the group count
+        for size in sorted({1, 2, min(3, len(sub)), min(5, len(sub)), len(sub)}):
+            assert ctx.preferred_allocation(sub, [], size) == opol.Allocate(list(sub), [], size)[0], (gpus, mig, mask, size)
+        must = sub[-1:]
+        for size in (1, min(4, len(sub))):
+            assert ctx.preferred_allocation(sub, must, size) == opol.Allocate(list(sub), list(must), size)[0]
+        hist = ctx.partition_histogram()
+        strategy_single_ok = len(hist) <= 1
+        if strategy_single_ok:
+            assert ctx.resource_list("single") == oplug.getResourceList("single", root)[0]
+        assert ctx.resource_list("mixed") == oplug.getResourceList("mixed", root)[0]
