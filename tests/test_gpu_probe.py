@@ -632,20 +632,28 @@ def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
         assert all(r.healthy and r.gbs_ref > 0 and 0.95 < r.frac < 1.03 for r in rs), rs
         ref0 = rs[0].gbs_ref
         gbs = sorted(r.gbs for r in rs[4:])[10]                    # timed=False: gbs is on the verdict's in-kernel clock
+        # pass-to-pass the in-kernel rate moves by about +-1.5 %, so a single pass parked 1 % from the line may land on
+        # either side; what must hold is (a) EVERY verdict agrees with that pass's own measured fraction and floor, and
+        # (b) over 9 passes the stream parked at 0.81 is Healthy and the one parked at 0.79 Unhealthy
         for frac, want in ((0.81, True), (0.79, False), (0.81, True), (0.79, False)):
             ctx.probe_set_ref(0, gbs / frac)
-            for _ in range(3):
+            got = []
+            for _ in range(9):
                 (r,) = ctx.probe_health(timed=False)
-                assert r.healthy == want and abs(r.frac - frac) < 0.008, (frac, r)
                 assert r.mismatches == 0 and r.checksum == r.expected_checksum and r.err == 0
-                assert bool(r.flags & P._native.RES_SLOW) == (not want)
+                if abs(r.frac - 0.8) > 1e-4:
+                    assert r.healthy == (r.frac >= 0.8) and bool(r.flags & P._native.RES_SLOW) == (r.frac < 0.8), r
                 assert abs(r.min_gbs_applied - oprobe.health_floor(nbytes, r.gbs_ref)) < 1.0    # the oracle's floor rule
                 assert r.healthy == oprobe.probe_healthy(True, r.checksum, r.mismatches, nbytes // 4, r.seed,
-                                                         r.frac * r.gbs_ref, r.min_gbs_applied)
-        ctx.probe_set_ref(0, gbs / 0.79)
+                                                         r.frac * r.gbs_ref, r.min_gbs_applied) or abs(r.frac - 0.8) <= 1e-4
+                got.append(r)
+            fr = sorted(r.frac for r in got)
+            assert abs(fr[4] - frac) < 0.008, (frac, fr)
+            assert sum(r.healthy == want for r in got) >= 7, (frac, [(round(r.frac, 4), r.healthy) for r in got])
+        ctx.probe_set_ref(0, gbs / 0.75)                          # well clear of the line for the single ListAndWatch check
         wire, st = ctx.list_and_watch("gpu", P._native.LW_HEARTBEAT)
         assert [d.health for d in P.v1beta1.ListAndWatchResponse.FromString(wire).devices] == ["Unhealthy"]
-        assert 0.775 < st.probe_frac_min < 0.80 and st.probe_ms_device_max > 0
+        assert 0.73 < st.probe_frac_min < 0.77 and st.probe_ms_device_max > 0
         ctx.probe_set_ref(0, 0.0)                                   # back to the calibration
         (r,) = ctx.probe_health(timed=False)
         assert r.healthy and abs(r.gbs_ref - ref0) < 1.0
