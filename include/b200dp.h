@@ -144,7 +144,9 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     opens: calib=<K, default 3> warm non-advancing passes per GPU, best kept, then the maximum over the
  *                     GPUs of the same product and ring size, so a part that is already slow at start-up is judged
  *                     against its siblings>, ref_gbs=<pin the ceiling instead of calibrating, e.g. the site's measured
- *                     peak>, min_gbs=<absolute GB/s floor, overrides min_frac; default none>.  The fractional floor
+ *                     peak>, min_gbs=<absolute GB/s floor, overrides min_frac; default none>, slow_passes=<K consecutive
+ *                     below-floor passes make the device Unhealthy, default 1: the first; earlier ones only carry
+ *                     B2DP_RES_SLOW -- pass to pass the rate moves by about 1.5 %; integrity faults are never debounced>.  The fractional floor
  *                     applies to rings that stream from HBM (slot >= 128 MiB, above the 126 MB L2); a pass below the floor
  *                     on a GPU that another process is using at that moment (NVML) is flagged B2DP_RES_CONTENDED and judged
  *                     on integrity alone,

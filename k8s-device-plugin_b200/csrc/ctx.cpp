@@ -220,6 +220,7 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else if (p.first == "min_frac") cfg.min_frac = (float)atof(p.second.c_str());
             else if (p.first == "ref_gbs") cfg.ref_gbs = (float)atof(p.second.c_str());
             else if (p.first == "calib") cfg.calib = atoi(p.second.c_str());
+            else if (p.first == "slow_passes") cfg.slow_passes = atoi(p.second.c_str());
             else if (p.first == "probe") {
                 if (p.second == "inproc") cfg.probe_mode = 0;
                 else if (p.second == "helpers") cfg.probe_mode = 1;
@@ -257,13 +258,14 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
         if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");
         if (cfg.mig_bytes < 4096 || cfg.mig_bytes % 16) return fail(B2DP_E_INVAL, "mig_bytes must be a multiple of 16, >= 4096");
         // what every helper process inherits: the verdict-related options (the ring geometry is set per unit)
-        for (const char* k : {"min_gbs", "min_frac", "ref_gbs", "calib", "busy", "shrink_bytes", "ecc"}) {
+        for (const char* k : {"min_gbs", "min_frac", "ref_gbs", "calib", "slow_passes", "busy", "shrink_bytes", "ecc"}) {
             auto it = kv.find(k);
             if (it != kv.end()) cfg.passthrough += std::string(",") + k + "=" + it->second;
         }
         if (cfg.slots < 2 || cfg.slots > 4096) return fail(B2DP_E_INVAL, "slots must be in [2, 4096]");
         if (!(cfg.min_frac >= 0.f && cfg.min_frac <= 1.f)) return fail(B2DP_E_INVAL, "min_frac must be in [0, 1]");
         if (cfg.calib < 0 || cfg.calib > 64) return fail(B2DP_E_INVAL, "calib must be in [0, 64]");
+        if (cfg.slow_passes < 1 || cfg.slow_passes > 1000) return fail(B2DP_E_INVAL, "slow_passes must be in [1, 1000]");
         if (cfg.launchers < 1 || cfg.launchers > 2) return fail(B2DP_E_INVAL, "launchers must be 1 or 2");
         if (cfg.spin_us < 0 || cfg.spin_us > 100000) return fail(B2DP_E_INVAL, "spin_us must be in [0, 100000]");
         std::string err;

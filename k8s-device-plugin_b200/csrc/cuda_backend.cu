@@ -88,6 +88,7 @@ struct Gpu {
     int64_t vram = 0, sms = 0;
     bool mig_capable = false;
     float gbs_cal = 0.f;                  // best of the calibration passes at open (this device)
+    int slow_streak = 0;                  // consecutive passes below the floor (slow_passes= debounce)
     std::atomic<float> gbs_ref{0.f};      // the ceiling the GB/s floor is a fraction of (peer group max, ref_gbs=, or b2dp_probe_set_ref)
     std::array<unsigned long long, 32> bc{};  // host closed-form bit counts for n_vec*4 words (pattern_math.hpp)
     void* nvh = nullptr;                  // NVML device handle (optional)
@@ -971,8 +972,12 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         }
         o.min_gbs_applied = floor;
         bool fast_enough = gbs_span >= floor;
-        if (!fast_enough) {
+        if (fast_enough) g->slow_streak = 0;
+        else {
             o.flags |= B2DP_RES_SLOW;
+            // slow_passes=K: only the K-th consecutive slow pass is a verdict (a one-heartbeat dip is flagged, not failed);
+            // integrity faults are never debounced
+            if (++g->slow_streak < be->cfg.slow_passes) fast_enough = true;
             // Slow path only: a pass that shared HBM bandwidth with another process on the GPU says nothing about the
             // part.  NVML counts the compute processes; this one holds one context itself.
             unsigned cnt = 0;

@@ -675,6 +675,15 @@ def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
     with _open(P, nbytes, ",ref_gbs=9000") as ctx:
         (r,) = ctx.probe_health(timed=False)
         assert not r.healthy and r.flags & P._native.RES_SLOW       # ~6.5 of 9.0 TB/s = 0.72: below the line
+    # slow_passes=3: a dip is flagged at once but only the third consecutive slow pass is a verdict; a fast pass resets it
+    with _open(P, nbytes, ",slow_passes=3") as ctx:
+        seen = [ctx.probe_health(timed=False, grid_ctas=18)[0] for _ in range(4)]
+        assert all(r.flags & P._native.RES_SLOW for r in seen) and [r.healthy for r in seen] == [True, True, False, False]
+        assert ctx.probe_health(timed=False)[0].healthy
+        seen = [ctx.probe_health(timed=False, grid_ctas=18)[0] for _ in range(2)]
+        assert [r.healthy for r in seen] == [True, True]
+        ctx.probe_inject_fault(0, 5, 1)                             # integrity is never debounced
+        assert not ctx.probe_health(timed=False)[0].healthy
     # a ring that fits the L2 carries no fractional floor (the pass does not measure HBM)
     with _open(P, 16 * MiB) as ctx:
         (r,) = ctx.probe_health(timed=False)
