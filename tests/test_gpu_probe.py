@@ -644,8 +644,9 @@ def test_health_floor_is_80_percent_of_the_calibrated_ceiling(P):
                 if abs(r.frac - 0.8) > 1e-4:
                     assert r.healthy == (r.frac >= 0.8) and bool(r.flags & P._native.RES_SLOW) == (r.frac < 0.8), r
                 assert abs(r.min_gbs_applied - oprobe.health_floor(nbytes, r.gbs_ref)) < 1.0    # the oracle's floor rule
-                assert r.healthy == oprobe.probe_healthy(True, r.checksum, r.mismatches, nbytes // 4, r.seed,
-                                                         r.frac * r.gbs_ref, r.min_gbs_applied) or abs(r.frac - 0.8) <= 1e-4
+                if not got:     # the oracle's full verdict rule (it re-sums the 1 GiB pattern: once per setting is enough)
+                    assert r.healthy == oprobe.probe_healthy(True, r.checksum, r.mismatches, nbytes // 4, r.seed,
+                                                             r.frac * r.gbs_ref, r.min_gbs_applied) or abs(r.frac - 0.8) <= 1e-4
                 got.append(r)
             fr = sorted(r.frac for r in got)
             assert abs(fr[4] - frac) < 0.008, (frac, fr)
