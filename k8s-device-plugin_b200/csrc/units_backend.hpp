@@ -244,16 +244,6 @@ static inline int units_finish_start(Unit& u, int wait_ms, std::string& err) {
     return 1;
 }
 
-// Start u's helper and wait for it (context open).
-static inline bool units_start_helper(UnitsBackend* ub, Unit& u, std::string& err) {
-    if (!units_begin_start(ub, u, err)) return false;
-    for (;;) {
-        const int st = units_finish_start(u, 1000, err);
-        if (st > 0) return true;
-        if (st < 0) return false;
-    }
-}
-
 // ---- open -------------------------------------------------------------------------------------------------------------
 // Returns B2DP_OK and *out, or an error.  `want_helpers`: probe=helpers (or forced by MIG); false: probe=off.
 static inline int units_open(const CudaConfig& cfg, Nvml& nv, bool want_helpers, std::unique_ptr<UnitsBackend>* out, std::string& err) {
@@ -408,6 +398,7 @@ static inline int units_open(const CudaConfig& cfg, Nvml& nv, bool want_helpers,
             return B2DP_E_NOGPU;
         }
         size_t ok = 0;
+        // all children are started before any is waited for: N fresh CUDA processes come up in parallel
         for (size_t i = 0; i < ub->units.size(); ++i) {
             Unit& u = ub->units[i];
             const uint64_t bytes = u.mig_slot >= 0 ? std::min<uint64_t>(cfg.mig_bytes, cfg.bytes) : cfg.bytes;
@@ -415,14 +406,23 @@ static inline int units_open(const CudaConfig& cfg, Nvml& nv, bool want_helpers,
                            ",seed_index=" + std::to_string(i) + cfg.passthrough;
             const bool forced = std::find(cfg.break_devices.begin(), cfg.break_devices.end(), (int)i) != cfg.break_devices.end();
             std::string e2;
-            if (forced || !units_start_helper(ub.get(), u, e2)) {
+            if (forced || !units_begin_start(ub.get(), u, e2)) {
                 u.broken = true;
                 u.broken_reason = forced ? "setup failure injected (break=)" : e2;
-                u.last_healthy = 0;
-                err = u.broken_reason + " on " + u.dev.id;
-                continue;
             }
-            ++ok;
+        }
+        for (auto& u : ub->units) {
+            if (!u.broken) {
+                std::string e2;
+                int st = 0;
+                while ((st = units_finish_start(u, 1000, e2)) == 0) {}
+                if (st > 0) { ++ok; continue; }
+                u.broken = true;
+                u.broken_reason = e2;
+            }
+            u.last_healthy = 0;
+            err = u.broken_reason + " on " + u.dev.id;
+            logf(2, "%s could not be set up and will be reported Unhealthy: %s", u.dev.id.c_str(), u.broken_reason.c_str());
         }
         if (!ok) { for (auto& u : ub->units) units_kill(u); return B2DP_E_CUDA; }
         // the ceiling: ref_gbs= or the best calibration among units of the same product and ring size
