@@ -128,6 +128,7 @@ def test_mig_allocate_specs_and_runtime_ids(pkg, monkeypatch, stub, tmp_path):
         assert [c.name for c in resp.cdi_devices] == ["nvidia.com/gpu=MIG-00000000-0002-4000-8000-00000000b200",
                                                       "nvidia.com/gpu=MIG-00000001-0001-4000-8000-00000000b200"]
         assert [d.host_path for d in resp.devices] == [s for s in specs if s not in ("/dev/nvidia-caps/nvidia-cap100", "/dev/nvidia-caps/nvidia-cap101")]
+        assert resp.SerializeToString() == ctx.allocate_response(["amdgpu_xcp_2", "amdgpu_xcp_9"])     # protobuf's own canonical bytes
         info = pkg._native.ProbeInfo()
         assert pkg._native.lib.b2dp_probe_describe(ctx._h, 3, info) == 0      # "amdgpu_xcp_10": GPU 1, third instance
         assert info.uuid.decode() == "MIG-00000001-0002-4000-8000-00000000b200" and info.sm_count == 18 and info.via_helper == 0
