@@ -16,11 +16,21 @@ public:
 };
 
 int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err) {
-    if (cfg.probe_mode == 0) { err = "sanitizer build: no in-process cuda backend (probe=off / probe=helpers only)"; return B2DP_E_NOGPU; }
     auto be = std::make_unique<CudaBackend>();
     be->cfg = cfg;
     be->nvml.load();
-    int rc = units_open(cfg, be->nvml, cfg.probe_mode == 1, &be->units, err);
+    int mode = cfg.probe_mode;  // like cuda_backend.cu: a node with a MIG-enabled GPU is probed through helpers
+    if (mode == 0 && cfg.mig_auto && be->nvml.ok && be->nvml.device_count && be->nvml.handle_by_index && be->nvml.mig_mode) {
+        unsigned cnt = 0;
+        if (be->nvml.device_count(&cnt) == 0)
+            for (unsigned i = 0; i < cnt; ++i) {
+                void* h = nullptr;
+                unsigned cur = 0, pend = 0;
+                if (be->nvml.handle_by_index(i, &h) == 0 && be->nvml.mig_mode(h, &cur, &pend) == 0 && cur == 1) mode = 1;
+            }
+    }
+    if (mode == 0) { err = "sanitizer build: no in-process cuda backend (probe=off / probe=helpers only)"; return B2DP_E_NOGPU; }
+    int rc = units_open(cfg, be->nvml, mode == 1, &be->units, err);
     if (rc != B2DP_OK) return rc;
     char buf[96] = {0};
     if (be->nvml.driver_version && be->nvml.driver_version(buf, sizeof buf) == 0) be->driver_version = buf;
