@@ -175,6 +175,12 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     node while the caller enqueues its own (spin_us=<how long it keeps spinning after a fan-out or a
  *                     pre-arm, default 500>); measured neutral at 8 GPUs (the driver serialises launches), so off by
  *                     default.  pin=1: bind the calling thread of the fan-out to the CPUs local to its GPUs.
+ *                     prearm=0|1 (default 0; B2DP_PREARM in the environment sets the default): while a pass runs the next one
+ *                     is enqueued behind cuStreamWaitValue32 on a host-mapped doorbell (a stream wait occupies no SM), and
+ *                     the next heartbeat starts it with one host store per GPU instead of a launch: start-of-work latency
+ *                     13 us instead of 34 us after seconds of idle (profiles/r02_doorbell_vs_launch.csv).  Passes with
+ *                     non-default options, fault repairs, peek/poke/reset, the P2P matrix and close discard ("flush") an
+ *                     armed pass: it is rung, waited for and ignored, the ring state does not advance.
  *                     seed_index=<i>: (helpers) the enumeration index this one-device context stands for.
  *                     A GPU whose own setup fails (or that break=<i>+<j>, a test hook, names by enumeration index)
  *                     stays in the device list and is reported Unhealthy with B2DP_E_CUDA on every pass; the open
@@ -255,6 +261,8 @@ typedef struct b2dp_probe_result {
 #define B2DP_RES_NO_FLOOR 0x40u    /* no GB/s floor applied: the ring slot is below 128 MiB (a pass out of the L2 says nothing
                                       about HBM) and no absolute min_gbs was given */
 #define B2DP_RES_SLOW 0x80u        /* achieved GB/s was below min_gbs_applied */
+#define B2DP_RES_PREARMED 0x100u   /* prearm=1: this pass had been enqueued behind its doorbell while the previous one ran; the
+                                      heartbeat only rang the doorbell (no launch on its critical path) */
 #define B2DP_RES_XID 0x8u          /* xid=1: a critical Xid event was delivered for this device since open (or the
                                       last b2dp_probe_reset) => Unhealthy, sticky */
 

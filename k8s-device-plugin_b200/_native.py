@@ -36,7 +36,7 @@ PROBE_VARIANT_TMA, PROBE_VARIANT_R128 = 0, 1
 PROBE_VIA_WORKERS = 0x10
 PROBE_EVENT_TIMING = 0x20
 RES_SKIPPED_BUSY, RES_SHRUNK, RES_ECC, RES_XID, RES_SMALL_RING = 1, 2, 4, 8, 16
-RES_CONTENDED, RES_NO_FLOOR, RES_SLOW = 0x20, 0x40, 0x80
+RES_CONTENDED, RES_NO_FLOOR, RES_SLOW, RES_PREARMED = 0x20, 0x40, 0x80, 0x100
 LW_INITIAL, LW_HEARTBEAT, LW_EXTERNAL_SOURCE, LW_NO_PROBE, LW_LINK_CHECK = 1, 2, 4, 8, 16
 
 Id64 = C.c_char * 64

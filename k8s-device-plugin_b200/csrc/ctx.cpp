@@ -221,6 +221,7 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             else if (p.first == "ref_gbs") cfg.ref_gbs = (float)atof(p.second.c_str());
             else if (p.first == "calib") cfg.calib = atoi(p.second.c_str());
             else if (p.first == "slow_passes") cfg.slow_passes = atoi(p.second.c_str());
+            else if (p.first == "prearm") cfg.prearm = p.second != "0";
             else if (p.first == "probe") {
                 if (p.second == "inproc") cfg.probe_mode = 0;
                 else if (p.second == "helpers") cfg.probe_mode = 1;
@@ -255,10 +256,11 @@ extern "C" int b2dp_open(const char* uri, b2dp_ctx** out) {
             }
             else return fail(B2DP_E_INVAL, "unknown cuda: option " + p.first);
         }
+        if (!kv.count("prearm")) { const char* e = getenv("B2DP_PREARM"); if (e && *e) cfg.prearm = *e != '0'; }  // site / test-wide default
         if (cfg.bytes < 4096 || cfg.bytes % 16) return fail(B2DP_E_INVAL, "bytes must be a multiple of 16, >= 4096");
         if (cfg.mig_bytes < 4096 || cfg.mig_bytes % 16) return fail(B2DP_E_INVAL, "mig_bytes must be a multiple of 16, >= 4096");
         // what every helper process inherits: the verdict-related options (the ring geometry is set per unit)
-        for (const char* k : {"min_gbs", "min_frac", "ref_gbs", "calib", "slow_passes", "busy", "shrink_bytes", "ecc"}) {
+        for (const char* k : {"min_gbs", "min_frac", "ref_gbs", "calib", "slow_passes", "prearm", "busy", "shrink_bytes", "ecc"}) {
             auto it = kv.find(k);
             if (it != kv.end()) cfg.passthrough += std::string(",") + k + "=" + it->second;
         }

@@ -89,6 +89,14 @@ struct Gpu {
     bool mig_capable = false;
     float gbs_cal = 0.f;                  // best of the calibration passes at open (this device)
     int slow_streak = 0;                  // consecutive passes below the floor (slow_passes= debounce)
+    // prearm=1: the NEXT pass is enqueued in advance behind a stream wait on a host-mapped doorbell; a heartbeat then
+    // only stores to the doorbell (no launch on the critical path -- after seconds of idle a launch costs ~35 us)
+    bool armed = false;
+    unsigned long long armed_seq = 0;
+    uint32_t armed_seed = 0;
+    volatile unsigned int* bell_h = nullptr;
+    unsigned long long bell_d = 0;
+    cudaEvent_t done_ev = nullptr;        // recorded between pass k and the armed pass k+1: "pass k finished"
     std::atomic<float> gbs_ref{0.f};      // the ceiling the GB/s floor is a fraction of (peer group max, ref_gbs=, or b2dp_probe_set_ref)
     std::array<unsigned long long, 32> bc{};  // host closed-form bit counts for n_vec*4 words (pattern_math.hpp)
     void* nvh = nullptr;                  // NVML device handle (optional)
@@ -149,6 +157,8 @@ public:
     std::mutex bc_mu;
     std::unique_ptr<UnitsBackend> units;             // probe=helpers / probe=off / MIG: the NVML-driven half (units_backend.hpp)
     std::vector<std::unique_ptr<std::atomic<unsigned long long>>> unit_xid;  // xid=1 in units mode: one sticky latch per unit
+    void* libcuda = nullptr;                         // prearm=1: cuStreamWaitValue32 from the driver API (cudart is linked statically)
+    int (*wait32)(void* stream, unsigned long long addr, unsigned value, unsigned flags) = nullptr;
     std::unique_ptr<Launcher> launcher;              // launchers=2
     std::vector<size_t> caller_idx;                  // the GPUs the calling thread enqueues (all of them without a launcher)
     cpu_set_t caller_cpus;                           // pin=1: CPUs local to the caller's GPUs
@@ -251,6 +261,37 @@ static void probe_issue(Gpu* g, ProbeJobResult* r, uint32_t variant) {
     if (r->timed) cudaEventRecord(g->e1, g->stream);
 }
 
+// ---- prearm=1 ---------------------------------------------------------------------------------------------------------
+// While pass k runs, pass k+1 is enqueued behind `cuStreamWaitValue32(doorbell == seq)`: a stream wait occupies no SM.
+// The next heartbeat rings the doorbell (one host store per GPU) instead of launching: measured on B200
+// (tools/doorbell_probe.cu, profiles/r02_doorbell_vs_launch.csv) start-of-work latency is 6 vs 8 us back to back and
+// 13 vs 34 us after 2 s of idle -- the production shape, a heartbeat every few seconds.  An armed pass that is not
+// wanted (fault repair, peek/poke/reset, P2P, a pass with other options, close) is FLUSHED: rung, waited for, its
+// result ignored, the ring state not advanced -- it read and re-keyed exactly what the next ordinary pass will.
+static inline void probe_ring(Gpu* g, unsigned long long seq) { __atomic_store_n(g->bell_h, (unsigned int)seq, __ATOMIC_RELEASE); }
+
+static void probe_arm(CudaBackend* be, Gpu* g) {  // g's device is current; pass k has just been enqueued on g->stream
+    if (!be->wait32 || g->armed) return;
+    const uint32_t seed = g->seed * 1664525u + 1013904223u, next = seed * 1664525u + 1013904223u;  // the state AFTER pass k
+    const int M = (int)g->buf.size(), src = (g->cur + 1) % M, dst = (g->cur + 2) % M;
+    cudaEventRecord(g->done_ev, g->stream);
+    const unsigned long long seq = g->seq + 1;
+    if (be->wait32((void*)g->stream, g->bell_d, (unsigned int)seq, 1u /*CU_STREAM_WAIT_VALUE_EQ*/) != 0) return;
+    g->seq = seq;
+    launch_probe(g, g->n_vec, 0u, seed, seed ^ next, g->buf[src], g->buf[dst], seq);
+    if (cudaGetLastError() != cudaSuccess) { probe_ring(g, seq); return; }  // release the wait; nothing follows it
+    g->armed = true;
+    g->armed_seq = seq;
+    g->armed_seed = seed;
+}
+
+static void probe_flush(Gpu* g) {  // discard the armed pass (see above); needs no current device
+    if (!g->armed) return;
+    probe_ring(g, g->armed_seq);
+    cudaStreamSynchronize(g->stream);
+    g->armed = false;
+}
+
 // The last CTA publishes the result block and, after a system-scope fence, the launch's sequence
 // number into pinned host memory (hbm_probe.cuh finish()): seeing the number means every CTA's
 // stores and the whole block are done -- completion without a driver call.
@@ -274,6 +315,7 @@ static void probe_collect(Gpu* g, ProbeJobResult* r) {
     if (!r->advance) {
         if (r->out.mismatches != 0 || !r->seq_ok) {  // repair the source buffer in place
             cudaSetDevice(g->ordinal);
+            probe_flush(g);
             hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
             cudaStreamSynchronize(g->stream);
         }
@@ -285,6 +327,7 @@ static void probe_collect(Gpu* g, ProbeJobResult* r) {
         // report once, then start the next pass from a clean pattern: a transient flip is
         // reported exactly once, a stuck cell shows up again on the next pass
         cudaSetDevice(g->ordinal);
+        probe_flush(g);  // the armed pass would read the buffer about to be repaired: discard it first
         hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], n_vec, g->seed);
         cudaStreamSynchronize(g->stream);
     }
@@ -548,6 +591,16 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
             TRY(cudaHostAlloc(&g->out_h, sizeof(ProbeOut), cudaHostAllocMapped));
             memset(g->out_h, 0, sizeof(ProbeOut));
             TRY(cudaHostGetDevicePointer(&g->out_d, g->out_h, 0));
+            {   // doorbell for prearm=1 (allocated always: 64 bytes)
+                void* bell = nullptr;
+                void* bell_dev = nullptr;
+                TRY(cudaHostAlloc(&bell, 64, cudaHostAllocMapped));
+                memset(bell, 0, 64);
+                TRY(cudaHostGetDevicePointer(&bell_dev, bell, 0));
+                g->bell_h = static_cast<volatile unsigned int*>(bell);
+                g->bell_d = (unsigned long long)(uintptr_t)bell_dev;
+                TRY(cudaEventCreateWithFlags(&g->done_ev, cudaEventDisableTiming));
+            }
             TRY(cudaFuncSetAttribute(hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem));
             TRY(cudaFuncSetAttribute(hbm_probe_tma<kTmaCW, kTmaTileVec, kTmaStages>,
@@ -627,6 +680,15 @@ int cuda_backend_open(const CudaConfig& cfg, CudaBackend** out, std::string& err
              (int)g->buf.size(), (unsigned long long)(g->n_vec * 16 >> 20), g->small_ring ? " (shrunk: HBM was short)" : "", g->gbs_cal, ref,
              cfg.min_gbs > 0 ? cfg.min_gbs : cfg.min_frac * ref);
     }
+    if (cfg.prearm && cfg.launchers < 2) {
+        be->libcuda = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (be->libcuda) {
+            void* f = dlsym(be->libcuda, "cuStreamWaitValue32_v2");
+            if (!f) f = dlsym(be->libcuda, "cuStreamWaitValue32");
+            be->wait32 = reinterpret_cast<int (*)(void*, unsigned long long, unsigned, unsigned)>(f);
+        }
+        if (!be->wait32) logf(1, "prearm=1: cuStreamWaitValue32 is not available; passes are launched at each heartbeat");
+    }
     // launchers=2: split the GPUs by NUMA node (GPU 0's node stays with the caller; one NUMA node: split in halves)
     for (size_t i = 0; i < be->gpus.size(); ++i) be->caller_idx.push_back(i);
     if (cfg.launchers >= 2 && be->gpus.size() >= 2) {
@@ -677,7 +739,10 @@ void cuda_backend_close(CudaBackend* be) {
         Gpu* g = gp.get();
         if (!g->th.joinable()) continue;
         post(g, [g] {
+            probe_flush(g);
             if (g->stream) cudaStreamSynchronize(g->stream);
+            if (g->bell_h) cudaFreeHost(const_cast<unsigned int*>(g->bell_h));
+            if (g->done_ev) cudaEventDestroy(g->done_ev);
             for (uint4* b : g->buf) if (b) cudaFree(b);
             if (g->ctl) cudaFree(g->ctl);
             if (g->out_h) cudaFreeHost(g->out_h);
@@ -690,6 +755,7 @@ void cuda_backend_close(CudaBackend* be) {
         g->th.join();
     }
     if (be->xid_set && be->nvml.event_set_free) be->nvml.event_set_free(be->xid_set);
+    if (be->libcuda) dlclose(be->libcuda);
     delete be;
 }
 
@@ -821,6 +887,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
     std::vector<std::shared_ptr<ProbeJobResult>> res(n);
     std::vector<std::shared_ptr<Completion>> cs(n);
     std::vector<char> state(n, 0);  // 0 pending, 1 done, 2 timed out / busy
+    std::vector<char> rung_any(n, 0);  // prearm=1: this pass was already enqueued and only had its doorbell rung
     const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms);
     for (size_t i = 0; i < n; ++i) { res[i] = std::make_shared<ProbeJobResult>(); res[i]->timed = timed; res[i]->grid = grid; }
     for (size_t i = 0; i < n; ++i) if (be->gpus[i]->broken) state[i] = 4;  // never launched on
@@ -854,6 +921,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             if (g->inflight.load()) { state[i] = 2; continue; }
             g->inflight.store(true);  // until collected: a pass that misses the deadline still owns seed/ring state
             cs[i] = post(g, [g, r, variant] {
+                probe_flush(g);
                 probe_issue(g, r.get(), variant);
                 if (r->ce == cudaSuccess) r->ce = cudaStreamSynchronize(g->stream);
                 probe_collect(g, r.get());
@@ -880,11 +948,25 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             cmd = L->cmd.fetch_add(1) + 1;  // seq_cst: ordered against the `sleeping` load below (store/load pair on both sides)
             if (L->sleeping.load()) { std::lock_guard<std::mutex> l(L->mu); L->cv.notify_one(); }
         }
+        // prearm=1: a pass with the default options may be the one that is already enqueued behind its doorbell
+        const bool can_arm = be->wait32 && variant == B2DP_PROBE_VARIANT_TMA && !timed && grid == 0 && be->cfg.busy_policy == 0;
+        auto armable = [&](size_t i) { return can_arm && res[i]->n_vec == 0 && res[i]->advance; };
+        std::vector<char> rung(n, 0);
+        for (size_t i : be->caller_idx) {  // doorbells first: one host store each, every armed GPU starts within microseconds
+            Gpu* g = be->gpus[i].get();
+            if (state[i] != 0 || !g->armed || !armable(i) || g->inflight.load()) continue;
+            ProbeJobResult* r = res[i].get();
+            r->n_vec = g->n_vec; r->seed = g->armed_seed; r->seq = g->armed_seq; r->ce = cudaSuccess;
+            probe_ring(g, g->armed_seq);
+            g->armed = false;
+            rung[i] = rung_any[i] = 1;
+        }
         for (size_t i : be->caller_idx) {
             Gpu* g = be->gpus[i].get();
-            if (state[i] != 0) continue;
+            if (state[i] != 0 || rung[i]) continue;
             if (g->inflight.load()) { state[i] = 2; continue; }
             cudaSetDevice(g->ordinal);
+            probe_flush(g);  // an armed pass that does not fit this call's options is discarded
             probe_issue(g, res[i].get(), variant);
         }
         if (L) while (L->done.load(std::memory_order_acquire) != cmd) {
@@ -892,6 +974,14 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             __builtin_ia32_pause();
 #endif
         }
+        // while the passes run: enqueue the NEXT one behind its doorbell (overlapped with ~0.33 ms of GPU work)
+        if (can_arm)
+            for (size_t i : be->caller_idx) {
+                Gpu* g = be->gpus[i].get();
+                if (state[i] != 0 || !armable(i) || res[i]->ce != cudaSuccess) continue;
+                cudaSetDevice(g->ordinal);
+                probe_arm(be, g);
+            }
         size_t pending = 0;
         for (size_t i = 0; i < n; ++i) pending += state[i] == 0;
         unsigned spins = 0;
@@ -920,8 +1010,10 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
             auto r = res[i];
             g->inflight.store(true);
             post(g, [g, r] {
-                if (r->ce == cudaSuccess) r->ce = cudaStreamSynchronize(g->stream);
+                // with a pass armed behind this one, "this pass is done" is the event recorded between the two
+                if (r->ce == cudaSuccess) r->ce = g->armed ? cudaEventSynchronize(g->done_ev) : cudaStreamSynchronize(g->stream);
                 probe_collect(g, r.get());
+                probe_flush(g);
                 g->inflight.store(false);
             });
         }
@@ -934,7 +1026,7 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         o.device = (int)i;
         o.bytes = 2ull * be->gpus[i]->n_vec * 16;
         o.first_bad_word = ~0ull;
-        o.flags = rflags[i] | (be->gpus[i]->small_ring ? B2DP_RES_SMALL_RING : 0u);
+        o.flags = rflags[i] | (be->gpus[i]->small_ring ? B2DP_RES_SMALL_RING : 0u) | (!via_workers && rung_any[i] ? B2DP_RES_PREARMED : 0u);
         if (state[i] == 2) { o.err = B2DP_E_TIMEOUT; o.healthy = 0; be->gpus[i]->last_healthy = 0; continue; }
         if (state[i] == 3) { o.bytes = 0; o.healthy = be->gpus[i]->last_healthy; continue; }  // skipped: last verdict stands
         if (state[i] == 4) { o.bytes = 0; o.err = B2DP_E_CUDA; o.healthy = 0; err = be->gpus[i]->broken_reason + " on " + be->gpus[i]->dev.id; continue; }
@@ -1072,6 +1164,7 @@ int cuda_inject_fault(CudaBackend* be, int device, uint64_t word, uint32_t mask,
     if (word >= g->n_vec * 4) { err = "word index out of range"; return B2DP_E_INVAL; }
     cudaError_t ce = cudaSuccess;
     run_sync(g, [&] {
+        probe_flush(g);
         hbm_poke<<<1, 1, 0, g->stream>>>(reinterpret_cast<uint32_t*>(g->buf[g->cur]), word, mask);
         ce = cudaStreamSynchronize(g->stream);
     });
@@ -1100,6 +1193,7 @@ int cuda_probe_reset(CudaBackend* be, int device, std::string& err) {
         g->xid_fault.store(0);  // operator acknowledgement: a latched Xid is cleared together with the buffers
         cudaError_t ce = cudaSuccess;
         run_sync(g, [&] {
+            probe_flush(g);
             hbm_fill<256><<<(int)g->sms * 8, 256, 0, g->stream>>>(g->buf[g->cur], g->n_vec, g->seed);
             ce = cudaStreamSynchronize(g->stream);
         });
@@ -1129,6 +1223,7 @@ int cuda_probe_peek(CudaBackend* be, int device, uint64_t word, uint32_t* out, u
     if (word + n > g->n_vec * 4) { err = "range out of bounds"; return B2DP_E_INVAL; }
     cudaError_t ce = cudaSuccess;
     run_sync(g, [&] {
+        probe_flush(g);
         ce = cudaMemcpyAsync(out, reinterpret_cast<const uint32_t*>(g->buf[g->cur]) + word, n * 4, cudaMemcpyDeviceToHost,
                              g->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(g->stream);
@@ -1242,9 +1337,10 @@ int cuda_p2p_matrix(CudaBackend* be, const b2dp_p2p_opts* opts, float* gbs, int3
     const unsigned long long n_vec = bytes / 16;
     const int iters = opts && opts->iters ? (int)opts->iters : 2;
     for (int i = 0; i < n * n; ++i) { gbs[i] = 0; link_type[i] = 0; mism[i] = 0; }
-    // a probe pass that missed its deadline still owns its GPU's seed/ring state: let the workers drain
+    // a probe pass that missed its deadline still owns its GPU's seed/ring state: let the workers drain; an armed
+    // pass (prearm=1) is discarded, the matrix uses every stream and the spare buffers
     for (auto& g : be->gpus)
-        if (g->inflight.load()) run_sync(g.get(), [] {});
+        if (!g->broken && g->th.joinable()) { Gpu* gp = g.get(); run_sync(gp, [gp] { probe_flush(gp); }); }
     const std::array<unsigned long long, 32>& bc = host_bitcounts(be, n_vec * 4);  // host closed form
 
     // peer capability + enable (on the reader's worker)

@@ -103,6 +103,7 @@ struct CudaConfig {
     float min_frac = 0.8f;               // Healthy needs >= min_frac x gbs_ref (BASELINE.json: ">= 80 % of HBM peak")
     float ref_gbs = 0.f;                 // the ceiling, if the operator pins it; 0 = calibrate at open
     int calib = 3;                       // calibration passes per GPU at open (best kept)
+    bool prearm = false;                 // enqueue the next pass behind a doorbell while the current one runs (see cuda_backend.cu)
     int slow_passes = 1;                 // consecutive below-floor passes that make a device Unhealthy (1 = the first one)
     int launchers = 1;                   // 2: a helper thread enqueues the other NUMA node's GPUs in parallel with the caller
     int spin_us = 500;                   // how long the helper keeps spinning after a fan-out / a pre-arm before it sleeps
