@@ -950,7 +950,9 @@ int cuda_probe(CudaBackend* be, const b2dp_probe_opts* opts, std::vector<b2dp_pr
         }
         // prearm=1: a pass with the default options may be the one that is already enqueued behind its doorbell
         const bool can_arm = be->wait32 && variant == B2DP_PROBE_VARIANT_TMA && !timed && grid == 0 && be->cfg.busy_policy == 0;
-        auto armable = [&](size_t i) { return can_arm && res[i]->n_vec == 0 && res[i]->advance; };
+        std::vector<char> arm_ok(n, 0);  // decided before any pass is issued (issuing fills in r->n_vec)
+        for (size_t i = 0; i < n; ++i) arm_ok[i] = can_arm && res[i]->n_vec == 0 && res[i]->advance;
+        auto armable = [&](size_t i) { return arm_ok[i] != 0; };
         std::vector<char> rung(n, 0);
         for (size_t i : be->caller_idx) {  // doorbells first: one host store each, every armed GPU starts within microseconds
             Gpu* g = be->gpus[i].get();

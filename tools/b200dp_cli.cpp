@@ -6,10 +6,11 @@
 //   g++ -O2 -std=c++17 -I include tools/b200dp_cli.cpp -L k8s-device-plugin_b200 -lb200dp \
 //       -Wl,-rpath,'$ORIGIN/../k8s-device-plugin_b200' -o tools/b200dp_cli
 //
-//   b200dp_cli <backend-uri> enumerate | health | cycle [steps] | probe [steps] | resources <single|mixed>
+//   b200dp_cli <backend-uri> enumerate | health | cycle [steps [idle_ms]] | probe [steps] | resources <single|mixed>
 //                            | labels <csv> | alloc <size> | p2p
 #include <algorithm>
 #include <chrono>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +60,7 @@ int main(int argc, char** argv) {
         printf("node %s\n", h ? "Healthy" : "Unhealthy");
     } else if (cmd == "probe" || cmd == "cycle") {
         const int steps = argc > 3 ? atoi(argv[3]) : 200;
+        const int idle_ms = argc > 4 ? atoi(argv[4]) : 0;  // sleep between cycles: the production shape is a heartbeat every few seconds
         std::vector<b2dp_probe_result> res(n ? n : 1);
         std::vector<uint8_t> buf(1 << 16);
         b2dp_cycle_opts co{};
@@ -70,6 +72,7 @@ int main(int argc, char** argv) {
         std::vector<double> wall, kern, kmax, host;
         double bytes = 0, frac_min = 1e30;
         for (int i = -5; i < steps; ++i) {
+            if (idle_ms > 0) { struct timespec ts{idle_ms / 1000, (long)(idle_ms % 1000) * 1000000L}; nanosleep(&ts, nullptr); }
             const double t0 = now_ms();
             if (cmd == "probe") {
                 int m = 0;
@@ -91,11 +94,11 @@ int main(int argc, char** argv) {
             }
         }
         const double w = median(wall);
-        printf("{\"command\": \"%s\", \"n_devices\": %d, \"steps\": %d, \"wall_ms_median\": %.4f, \"wall_ms_p99\": %.4f, "
+        printf("{\"command\": \"%s\", \"idle_ms_between_cycles\": %d, \"n_devices\": %d, \"steps\": %d, \"wall_ms_median\": %.4f, \"wall_ms_p99\": %.4f, "
                "\"wall_ms_max\": %.4f, \"aggregate_gbs\": %.1f, \"kernel_ms_median\": %.4f, \"response_bytes\": %zu, "
                "\"slowest_kernel_ms_p50\": %.4f, \"slowest_kernel_ms_p99\": %.4f, \"host_overhead_ms_p50\": %.4f, "
                "\"host_overhead_ms_p99\": %.4f, \"probe_frac_min\": %.4f}\n",
-               cmd.c_str(), n, steps, w, pct(wall, 0.99), *std::max_element(wall.begin(), wall.end()), bytes / w / 1e6,
+               cmd.c_str(), idle_ms, n, steps, w, pct(wall, 0.99), *std::max_element(wall.begin(), wall.end()), bytes / w / 1e6,
                median(kern), len, pct(kmax, 0.5), pct(kmax, 0.99), pct(host, 0.5), pct(host, 0.99), frac_min > 1e29 ? 0.0 : frac_min);
     } else if (cmd == "resources") {
         char names[16][64];
