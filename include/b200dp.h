@@ -180,7 +180,10 @@ typedef struct b2dp_ctx b2dp_ctx;
  *                     the next heartbeat starts it with one host store per GPU instead of a launch: start-of-work latency
  *                     13 us instead of 34 us after seconds of idle (profiles/r02_doorbell_vs_launch.csv).  Passes with
  *                     non-default options, fault repairs, peek/poke/reset, the P2P matrix and close discard ("flush") an
- *                     armed pass: it is rung, waited for and ignored, the ring state does not advance.
+ *                     armed pass: it is rung, waited for and ignored, the ring state does not advance.  CONSTRAINT: while a
+ *                     pass is armed, its stream wait stalls all other GPU work THIS PROCESS submits to that GPU (other streams,
+ *                     a second context of this library; measured) -- other processes are not affected (a tenant's kernels
+ *                     keep their latency).  Use it only where the library is the process's sole user of the GPU (the daemon).
  *                     seed_index=<i>: (helpers) the enumeration index this one-device context stands for.
  *                     A GPU whose own setup fails (or that break=<i>+<j>, a test hook, names by enumeration index)
  *                     stays in the device list and is reported Unhealthy with B2DP_E_CUDA on every pass; the open

@@ -268,6 +268,9 @@ static void probe_issue(Gpu* g, ProbeJobResult* r, uint32_t variant) {
 // 13 vs 34 us after 2 s of idle -- the production shape, a heartbeat every few seconds.  An armed pass that is not
 // wanted (fault repair, peek/poke/reset, P2P, a pass with other options, close) is FLUSHED: rung, waited for, its
 // result ignored, the ring state not advanced -- it read and re-keyed exactly what the next ordinary pass will.
+// Off by default: a pending stream wait stalls every OTHER piece of work this process submits to the same GPU (other
+// streams, a second context -- measured; other processes keep their latency), so it belongs in a process whose only GPU
+// user is this library.
 static inline void probe_ring(Gpu* g, unsigned long long seq) { __atomic_store_n(g->bell_h, (unsigned int)seq, __ATOMIC_RELEASE); }
 
 static void probe_arm(CudaBackend* be, Gpu* g) {  // g's device is current; pass k has just been enqueued on g->stream
