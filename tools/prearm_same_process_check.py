@@ -1,3 +1,10 @@
+#!/usr/bin/env python3
+"""What a pending prearm=1 doorbell wait does to OTHER work this process submits to the same GPU (the reason prearm is
+opt-in): arms one pass, then tries torch work on the default and side streams and a second library context, each with a
+time limit, then rings the doorbell.  Result of round 2: profiles/r02_prearm_same_process_constraint.txt.
+
+    gpurun -- python tools/prearm_same_process_check.py [n_extra_streams]
+"""
 import importlib, sys, time, threading, os
 sys.path.insert(0, "/root/repo")
 import torch
