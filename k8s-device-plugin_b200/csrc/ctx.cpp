@@ -718,7 +718,7 @@ static int device_specs(b2dp_ctx* c, const char* const* ids, int n_ids, std::vec
                 if (!cuda_device_paths(c->cuda, d.id, paths)) paths.push_back("/dev/nvidia" + std::to_string(d.card));
                 for (auto& pth : paths) {
                     bool dup = false;  // instances of one GPU share the parent's node
-                    for (auto& have : specs) dup = dup || pth == have.host_path;
+                    for (auto& spec : specs) dup = dup || pth == spec.host_path;
                     if (!dup) push(pth);
                 }
             }
