@@ -12,4 +12,4 @@ bench: build             # needs a B200
 clean:
 	$(MAKE) -C k8s-device-plugin_b200/csrc clean
 	$(MAKE) -C oracle clean
-	rm -f tools/probe_sweep tools/p2p_sweep tools/b200dp_cli tools/b200dp_kubelet_sim k8s-device-plugin_b200/b200dp_plugind
+	rm -f tools/probe_sweep tools/p2p_sweep tools/doorbell_probe tools/b200dp_cli tools/b200dp_kubelet_sim k8s-device-plugin_b200/b200dp_plugind k8s-device-plugin_b200/b200dp_probe_helper
