@@ -30,9 +30,11 @@ def stub():
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(HERE, "native", "nvml_stub.cpp")
     if not os.path.exists(STUB) or os.path.getmtime(src) > os.path.getmtime(STUB):
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fvisibility=hidden", src, "-o", STUB],
+        tmp = "%s.tmp%d" % (STUB, os.getpid())                     # atomic: xdist workers may build at once
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fvisibility=hidden", src, "-o", tmp],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+        os.replace(tmp, STUB)
     return STUB
 
 
@@ -228,8 +230,10 @@ def fake_helper():
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(HERE, "native", "fake_probe_helper.cpp")
     if not os.path.exists(FAKE) or os.path.getmtime(src) > os.path.getmtime(FAKE):
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", src, "-o", FAKE], capture_output=True, text=True)
+        tmp = "%s.tmp%d" % (FAKE, os.getpid())
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", src, "-o", tmp], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+        os.replace(tmp, FAKE)
     return FAKE
 
 

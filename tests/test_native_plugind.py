@@ -463,8 +463,10 @@ def test_native_daemon_on_a_mig_node_end_to_end(pkg, short_dir, tmp_path):
         os.makedirs(tm.BUILD, exist_ok=True)
         srcp = os.path.join(HERE, "native", src)
         if not os.path.exists(out) or os.path.getmtime(srcp) > os.path.getmtime(out):
-            r = subprocess.run(["g++", "-std=c++17", "-O1"] + extra + [srcp, "-o", out], capture_output=True, text=True)
+            tmp = "%s.tmp%d" % (out, os.getpid())
+            r = subprocess.run(["g++", "-std=c++17", "-O1"] + extra + [srcp, "-o", tmp], capture_output=True, text=True)
             assert r.returncode == 0, r.stderr
+            os.replace(tmp, out)
     env = dict(os.environ, B2DP_NVML_LIBRARY=tm.STUB, B2DP_NVML_STUB="gpus=2,mig=3,migmask=1", B2DP_PROBE_HELPER=tm.FAKE)
     plug_dir = short_dir
     kubelet = FakeKubelet(os.path.join(plug_dir, "kubelet.sock"), V)

@@ -44,10 +44,10 @@ def _build(out, flags, sources=None, werror=True):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fno-omit-frame-pointer", "-Wall"] + (["-Werror"] if werror else []) + \
-          flags + list(sources) + ["-o", out + ".tmp", "-lpthread", "-ldl"]
+          flags + list(sources) + ["-o", out + ".tmp%d" % os.getpid(), "-lpthread", "-ldl"]   # unique: xdist workers may build at once
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
-    os.replace(out + ".tmp", out)
+    os.replace(out + ".tmp%d" % os.getpid(), out)
     return out
 
 
@@ -127,9 +127,11 @@ def test_mig_enumeration_under_sanitizers(bins, which, tmp_path):
     os.makedirs(tm.BUILD, exist_ok=True)
     src = os.path.join(HERE, "native", "nvml_stub.cpp")
     if not os.path.exists(stub) or os.path.getmtime(src) > os.path.getmtime(stub):
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fvisibility=hidden", src, "-o", stub],
+        tmp = "%s.tmp%d" % (stub, os.getpid())
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fvisibility=hidden", src, "-o", tmp],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+        os.replace(tmp, stub)
     env = _env()
     env["B2DP_NVML_LIBRARY"] = stub
     env["B2DP_NVML_STUB"] = "gpus=8,mig=7"
@@ -150,8 +152,10 @@ def test_helper_fan_out_under_sanitizers(bins, which, tmp_path):
         os.makedirs(tm.BUILD, exist_ok=True)
         srcp = os.path.join(HERE, "native", src)
         if not os.path.exists(out) or os.path.getmtime(srcp) > os.path.getmtime(out):
-            r = subprocess.run(["g++", "-std=c++17", "-O1"] + extra + [srcp, "-o", out], capture_output=True, text=True)
+            tmp = "%s.tmp%d" % (out, os.getpid())
+            r = subprocess.run(["g++", "-std=c++17", "-O1"] + extra + [srcp, "-o", tmp], capture_output=True, text=True)
             assert r.returncode == 0, r.stderr
+            os.replace(tmp, out)
     env = _env()
     env.update(B2DP_NVML_LIBRARY=tm.STUB, B2DP_NVML_STUB="gpus=2,mig=3", B2DP_PROBE_HELPER=tm.FAKE)
     uri = "cuda:probe=helpers,mig_bytes=1048576,sysroot=" + tm._sysroot(tmp_path, 2, 3)
