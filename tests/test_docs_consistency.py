@@ -47,3 +47,24 @@ def test_header_cites_the_reference_for_every_entry_point():
         block = head[head.rfind("\n\n"):] if "\n\n" in head[-3000:] else head[-1500:]
         cited = re.search(r"\b[\w/\-]+\.(go|proto):\d+", block) is not None
         assert cited or name in own, name
+
+
+def test_every_backend_option_is_documented():
+    """Every `cuda:` URI key the parser accepts (csrc/ctx.cpp) is described in include/b200dp.h and listed in USAGE.md
+    (`break` and `seed_index` are a test hook and an internal hand-over, documented in the header only)."""
+    src = open(os.path.join(ROOT, "k8s-device-plugin_b200", "csrc", "ctx.cpp")).read()
+    a = src.index('if (u.compare(0, 5, "cuda:") == 0) {')
+    b = src.index('return fail(B2DP_E_INVAL, "unknown cuda: option "')
+    keys = set(re.findall(r'p\.first == "([a-z_0-9]+)"', src[a:b]))
+    assert len(keys) >= 25, keys
+    hdr = open(os.path.join(ROOT, "include", "b200dp.h")).read()
+    usage = open(os.path.join(ROOT, "USAGE.md")).read()
+    for k in sorted(keys):
+        assert re.search(r"\b%s=" % re.escape(k), hdr), "header does not describe cuda: option " + k
+        if k not in ("break", "seed_index"):
+            assert re.search(r"`%s[=`]" % re.escape(k), usage) or ("%s=" % k) in usage, "USAGE.md does not list " + k
+    # and the daemon's flags
+    d = open(os.path.join(ROOT, "k8s-device-plugin_b200", "csrc", "host", "plugind.cpp")).read()
+    flags = set(re.findall(r'name == "([a-z_]+)"', d)) | {"labels", "reconcile", "patch", "version"}
+    for f in sorted(flags):
+        assert ("-" + f) in usage, "USAGE.md does not list daemon flag -" + f
