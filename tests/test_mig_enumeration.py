@@ -432,3 +432,31 @@ def test_random_mig_layouts_equal_the_oracle_on_the_export(pkg, monkeypatch, stu
         if strategy_single_ok:
             assert ctx.resource_list("single") == oplug.getResourceList("single", root)[0]
         assert ctx.resource_list("mixed") == oplug.getResourceList("mixed", root)[0]
+
+
+def test_library_watch_loop_over_mig_helpers(pkg, monkeypatch, stub, fake_helper, tmp_path):
+    """b2dp_watch_* (the library-owned ListAndWatch loop with its -pulse ticker, plugin.go:229-330) on a MIG node probed
+    through helpers: initial list without a probe, then one verified cycle per 5 ms tick for the partition resource; a
+    fault injected into one instance shows up in exactly one response."""
+    import queue
+    N = pkg._native
+    monkeypatch.setenv("B2DP_NVML_LIBRARY", stub)
+    monkeypatch.setenv("B2DP_NVML_STUB", "gpus=2,mig=2")
+    monkeypatch.setenv("B2DP_PROBE_HELPER", fake_helper)
+    got = queue.Queue()
+    with pkg.Context("cuda:sysroot=%s,mig_bytes=%d" % (_sysroot(tmp_path, 2, 2), 1 << 20)) as ctx:
+        w = ctx.watch(lambda rc, wire, st: got.put((rc, wire, st)), resource="1g_23gb", pulse_ms=5)
+        try:
+            rc, wire, st = got.get(timeout=10)
+            assert rc == 0 and st.probe_bytes == 0 and st.n_devices == 4
+            healths = []
+            for i in range(8):
+                if i == 3:
+                    ctx.probe_inject_fault(2, 99, 1)
+                rc, wire, st = got.get(timeout=10)
+                assert rc == 0 and st.n_devices == 4 and st.probe_bytes == 4 * 2 * (1 << 20)
+                healths.append([d.health for d in pkg.v1beta1.ListAndWatchResponse.FromString(wire).devices])
+        finally:
+            w.stop()
+        bad = [h for h in healths if "Unhealthy" in h]
+        assert len(bad) == 1 and bad[0] == ["Healthy", "Healthy", "Unhealthy", "Healthy"], healths
