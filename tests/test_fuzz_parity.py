@@ -134,7 +134,7 @@ GENS = ["driver-version", "driver-src-version", "device-id", "product-name", "vr
         "compute-memory-partition", "compute-partitioning-supported", "memory-partitioning-supported", "family", "firmware"]
 
 
-@pytest.mark.parametrize("seed", range(140))
+@pytest.mark.parametrize("seed", range(400))
 def test_random_tree_parity(pkg, tmp_path, seed):
     rng = random.Random(0xB200 + seed)
     root = str(tmp_path / "t")
