@@ -59,7 +59,7 @@ def test_device_plugin_main_registers_and_beats(pkg, kfd, tmp_path, short_dir):
             _s.signal = orig
     th = threading.Thread(target=run, daemon=True)
     th.start()
-    regs = sorted((kubelet.requests.get(timeout=10) for _ in range(2)), key=lambda r: r.resource_name)
+    regs = sorted((kubelet.requests.get(timeout=30) for _ in range(2)), key=lambda r: r.resource_name)
     assert [r.resource_name for r in regs] == ["amd.com/cpx_nps1", "amd.com/spx_nps1"]      # heterogeneous + mixed
     assert [r.endpoint for r in regs] == ["amd.com_cpx_nps1", "amd.com_spx_nps1"]
     with grpc.insecure_channel("unix://" + os.path.join(plug_dir, "amd.com_cpx_nps1")) as ch:
@@ -78,7 +78,7 @@ def test_device_plugin_main_registers_and_beats(pkg, kfd, tmp_path, short_dir):
         os.unlink(sock)
     time.sleep(0.3)
     kubelet2 = FakeKubelet(sock, V)
-    regs = sorted((kubelet2.requests.get(timeout=15) for _ in range(2)), key=lambda r: r.resource_name)
+    regs = sorted((kubelet2.requests.get(timeout=30) for _ in range(2)), key=lambda r: r.resource_name)
     assert [r.resource_name for r in regs] == ["amd.com/cpx_nps1", "amd.com/spx_nps1"]
     with grpc.insecure_channel("unix://" + os.path.join(plug_dir, "amd.com_spx_nps1")) as ch:
         stream = ch.unary_stream(V.LIST_AND_WATCH, request_serializer=lambda m: m.SerializeToString(),

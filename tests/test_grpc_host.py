@@ -40,7 +40,7 @@ class FakeKubelet:
 
 def _call(ch, method, req, resp_cls):
     return ch.unary_unary(method, request_serializer=lambda m: m.SerializeToString(),
-                          response_deserializer=resp_cls.FromString)(req, timeout=10)
+                          response_deserializer=resp_cls.FromString)(req, timeout=30)
 
 
 def test_kubelet_round_trip(pkg, kfd, tmp_path, short_dir):
@@ -60,7 +60,7 @@ def test_kubelet_round_trip(pkg, kfd, tmp_path, short_dir):
         server = srv_mod.PluginServer(plugin, plugin_dir=plug_dir).start()
         try:
             server.register()
-            reg = kubelet.requests.get(timeout=5)
+            reg = kubelet.requests.get(timeout=30)
             assert (reg.version, reg.endpoint, reg.resource_name) == ("v1beta1", "amd.com_gpu", "amd.com/gpu")
             assert reg.options.get_preferred_allocation_available and not reg.options.pre_start_required
             assert os.path.exists(os.path.join(plug_dir, "amd.com_gpu"))

@@ -50,7 +50,7 @@ def test_native_daemon_kubelet_round_trip(daemon_env):
     proc = subprocess.Popen([EXE, "-pulse=1", "-resource_naming_strategy=single", "-backend=kfd:" + root,
                              "-plugin_dir", plug_dir], stderr=subprocess.PIPE, text=True)
     try:
-        reg = kubelet.requests.get(timeout=10)                 # the native gRPC client -> grpcio server
+        reg = kubelet.requests.get(timeout=30)                 # the native gRPC client -> grpcio server
         assert (reg.version, reg.endpoint, reg.resource_name) == ("v1beta1", "amd.com_gpu", "amd.com/gpu")
         assert reg.options.get_preferred_allocation_available and not reg.options.pre_start_required
         sock = os.path.join(plug_dir, "amd.com_gpu")
@@ -110,7 +110,7 @@ def test_native_daemon_kubelet_round_trip(daemon_env):
         if os.path.exists(os.path.join(plug_dir, "kubelet.sock")):
             os.unlink(os.path.join(plug_dir, "kubelet.sock"))
         kubelet = FakeKubelet(os.path.join(plug_dir, "kubelet.sock"), V)
-        reg = kubelet.requests.get(timeout=10)
+        reg = kubelet.requests.get(timeout=30)
         assert reg.resource_name == "amd.com/gpu"
         with grpc.insecure_channel("unix://" + sock) as ch:
             assert _call(ch, V.GET_OPTIONS, V.Empty(), V.DevicePluginOptions).get_preferred_allocation_available
@@ -184,7 +184,7 @@ def test_native_daemon_survives_hostile_peers(daemon_env):
             s.close()
 
     try:
-        kubelet.requests.get(timeout=10)
+        kubelet.requests.get(timeout=30)
         assert _wait_for(sock)
         rng = random.Random(7)
         hdr_ok = frame(4, 0, 0, b"")                                            # SETTINGS
@@ -255,7 +255,7 @@ def test_native_daemon_exporter_socket_on_kfd_is_a_clean_error(daemon_env):
     proc = subprocess.Popen([EXE, "-backend=kfd:" + root, "-plugin_dir", plug_dir, "-exporter_socket", exp],
                             stderr=subprocess.PIPE, text=True)
     try:
-        kubelet.requests.get(timeout=10)
+        kubelet.requests.get(timeout=30)
         assert _wait_for(exp)
         with grpc.insecure_channel("unix://" + exp) as ch:
             call = ch.unary_unary(srv_mod.METRICS_LIST, request_serializer=lambda b: b,
@@ -286,7 +286,7 @@ def test_native_daemon_soak_streams_come_and_go(daemon_env):
         return int(st["Threads"].split()[0]), int(st["VmRSS"].split()[0])
 
     try:
-        kubelet.requests.get(timeout=10)
+        kubelet.requests.get(timeout=30)
         assert _wait_for(sock)
         marks = []
         for it in range(60):
@@ -339,7 +339,7 @@ def test_native_daemon_mixed_strategy_two_resources(pkg, kfd, tmp_path, short_di
     proc = subprocess.Popen([EXE, "-resource_naming_strategy=mixed", "-backend=kfd:" + root, "-plugin_dir", short_dir],
                             stderr=subprocess.PIPE, text=True)
     try:
-        regs = sorted((kubelet.requests.get(timeout=10) for _ in range(2)), key=lambda q: q.resource_name)
+        regs = sorted((kubelet.requests.get(timeout=30) for _ in range(2)), key=lambda q: q.resource_name)
         assert [q.resource_name for q in regs] == ["amd.com/cpx_nps1", "amd.com/spx_nps1"]
         assert [q.endpoint for q in regs] == ["amd.com_cpx_nps1", "amd.com_spx_nps1"]
         for q in regs:
@@ -474,7 +474,7 @@ def test_native_daemon_on_a_mig_node_end_to_end(pkg, short_dir, tmp_path):
                              "-backend=cuda:mig_bytes=1048576,cdi=nvidia.com/gpu,sysroot=" + tm._sysroot(tmp_path, 2, 3)],
                             stderr=subprocess.PIPE, text=True, env=env)
     try:
-        regs = sorted((kubelet.requests.get(timeout=15) for _ in range(2)), key=lambda r: r.resource_name)
+        regs = sorted((kubelet.requests.get(timeout=30) for _ in range(2)), key=lambda r: r.resource_name)
         assert [r.resource_name for r in regs] == ["amd.com/1g_23gb", "amd.com/7g_179gb"]
         assert [r.endpoint for r in regs] == ["amd.com_1g_23gb", "amd.com_7g_179gb"]
         mig_ids = ["0000:19:00.0", "amdgpu_xcp_1", "amdgpu_xcp_2"]

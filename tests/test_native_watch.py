@@ -16,7 +16,7 @@ def test_watch_initial_beats_and_stop(pkg, kfd, tmp_path):
     got = queue.Queue()
     with pkg.Context("kfd:" + root) as ctx:
         w = ctx.watch(lambda rc, wire, st: got.put((rc, wire, st)), resource="gpu", flags=pkg._native.LW_NO_PROBE)
-        rc, wire, st = got.get(timeout=5)                     # stream start: the full list, all Healthy
+        rc, wire, st = got.get(timeout=30)                    # stream start: the full list, all Healthy
         assert rc == 0 and st.n_devices == 63
         assert [(d.ID, d.health, d.topology.nodes[0].ID) for d in V.ListAndWatchResponse.FromString(wire).devices] == want
         assert got.empty()                                    # nothing more until a tick
