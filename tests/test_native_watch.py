@@ -23,7 +23,7 @@ def test_watch_initial_beats_and_stop(pkg, kfd, tmp_path):
         w.beat()
         w.beat()
         for _ in range(2):
-            rc, wire2, st = got.get(timeout=5)
+            rc, wire2, st = got.get(timeout=30)
             assert rc == 0 and wire2 == wire and st.node_healthy
         w.stop()                                              # p.signal: the loop ends, the thread is joined
         assert got.empty()
@@ -36,7 +36,7 @@ def test_watch_ticker(pkg, tmp_path):
     with pkg.Context("kfd:" + root) as ctx:
         t0 = time.monotonic()
         w = ctx.watch(lambda rc, wire, st: got.put(time.monotonic()), pulse_ms=50, flags=pkg._native.LW_NO_PROBE)
-        stamps = [got.get(timeout=5) for _ in range(4)]       # initial + 3 ticks
+        stamps = [got.get(timeout=30) for _ in range(4)]       # initial + 3 ticks
         w.stop()
     assert stamps[0] - t0 < 3.0
     gaps = [b - a for a, b in zip(stamps, stamps[1:])]
@@ -54,7 +54,7 @@ def test_watch_heterogeneous_resource_without_devices_sends_nothing(pkg, kfd, tm
         w.stop()
         assert got.empty()                                    # plugin.go:296-298
         w = ctx.watch(lambda rc, wire, st: got.put((rc, st.n_devices)), resource="spx_nps1", flags=pkg._native.LW_NO_PROBE)
-        assert got.get(timeout=5) == (0, 16)
+        assert got.get(timeout=30) == (0, 16)
         w.stop()
 
 
@@ -76,6 +76,6 @@ def test_watch_can_be_stopped_from_its_own_callback(pkg, tmp_path):
                     time.sleep(0.001)
                 holder["w"].stop()                          # second send: stop from inside
         holder["w"] = ctx.watch(cb, pulse_ms=20, flags=pkg._native.LW_NO_PROBE)
-        assert got.get(timeout=5) > 0 and got.get(timeout=5) > 0
+        assert got.get(timeout=30) > 0 and got.get(timeout=30) > 0
         time.sleep(0.3)
         assert got.empty()                                  # no third send: the loop is gone
