@@ -5,6 +5,7 @@
 //   B2DP_NVML_STUB="gpus=8,mig=7"            8 GPUs, MIG enabled on all, 7 x 1g.23gb instances each
 //   B2DP_NVML_STUB="gpus=4,mig=3,migmask=5"  MIG enabled on GPUs 0 and 2 only (3 instances each), 1 and 3 whole
 //   B2DP_NVML_STUB="gpus=2,mig=0"            two whole GPUs; minors are reversed (minor != NVML index)
+//   B2DP_NVML_STUB="gpus=2,mig=3,empty=2"    GPU 1 has MIG mode enabled but no instance has been created on it
 // PCI layout = k8s-device-plugin_b200/synth.py:write_b200_tree: bus 0x19 + 0x10*g, device 0, domain 0.
 #include <cstdio>
 #include <cstdlib>
@@ -14,7 +15,7 @@ namespace {
 struct Dev { int gpu; int slot; };  // slot < 0: the physical GPU
 Dev g_gpu[16];
 Dev g_mig[16][8];
-int g_n = 8, g_mig_n = 7, g_mask = -1;
+int g_n = 8, g_mig_n = 7, g_mask = -1, g_empty = 0;  // g_empty: GPUs with MIG mode enabled but no instance created
 bool g_init = false;
 
 void configure() {
@@ -26,6 +27,7 @@ void configure() {
         if ((p = strstr(c, "gpus="))) g_n = atoi(p + 5);
         if ((p = strstr(c, "mig="))) g_mig_n = atoi(p + 4);
         if ((p = strstr(c, "migmask="))) g_mask = atoi(p + 8);
+        if ((p = strstr(c, "empty="))) g_empty = atoi(p + 6);
     }
     if (g_n < 1) g_n = 1;
     if (g_n > 16) g_n = 16;
@@ -81,7 +83,7 @@ API int nvmlDeviceGetGspFirmwareVersion(void*, char* v) { put(v, 64, "580.159.03
 API int nvmlDeviceGetMigMode(void* h, unsigned* cur, unsigned* pend) { *cur = *pend = mig_on(dev(h)->gpu) ? 1u : 0u; return 0; }
 API int nvmlDeviceGetMaxMigDeviceCount(void*, unsigned* n) { *n = 7; return 0; }
 API int nvmlDeviceGetMigDeviceHandleByIndex(void* h, unsigned idx, void** mh) {
-    if (!mig_on(dev(h)->gpu) || (int)idx >= g_mig_n) return 6;  // NVML_ERROR_NOT_FOUND
+    if (!mig_on(dev(h)->gpu) || (int)idx >= g_mig_n || ((g_empty >> dev(h)->gpu) & 1)) return 6;  // NVML_ERROR_NOT_FOUND
     *mh = &g_mig[dev(h)->gpu][idx];
     return 0;
 }

@@ -460,3 +460,16 @@ def test_library_watch_loop_over_mig_helpers(pkg, monkeypatch, stub, fake_helper
             w.stop()
         bad = [h for h in healths if "Unhealthy" in h]
         assert len(bad) == 1 and bad[0] == ["Healthy", "Healthy", "Unhealthy", "Healthy"], healths
+
+
+def test_mig_enabled_gpu_without_instances_lists_nothing(pkg, monkeypatch, stub, tmp_path):
+    """A GPU with MIG mode enabled but no instance created has nothing to schedule: it is not listed (the whole GPU is
+    not usable by CUDA in that state); a node where that leaves no device at all fails to open with a clear message."""
+    monkeypatch.setenv("B2DP_NVML_LIBRARY", stub)
+    monkeypatch.setenv("B2DP_NVML_STUB", "gpus=2,mig=3,empty=2")
+    with pkg.Context("cuda:probe=off,sysroot=%s" % _sysroot(tmp_path, 2, 3)) as ctx:
+        assert sorted(ctx.enumerate()) == ["0000:19:00.0", "amdgpu_xcp_1", "amdgpu_xcp_2"]
+    monkeypatch.setenv("B2DP_NVML_STUB", "gpus=2,mig=3,empty=3")
+    with pytest.raises(pkg._native.B2dpError) as ei:
+        pkg.Context("cuda:probe=off,sysroot=%s" % _sysroot(tmp_path, 2, 3))
+    assert ei.value.code == pkg._native.E_NOGPU and "no instance" in str(ei.value)
