@@ -10,8 +10,10 @@ ordering, unanchored RE2 matches, strconv.ParseInt base-0 rules, bufio.Scanner
 line splitting, map-iteration nondeterminism) are restated in `oracle.gosem`.
 
 Who may import this package: `tests/`, `__graft_entry__.smoke()` and the
-`cpu_baseline` / `--impl reference` legs of `bench.py` -- as the checker or as
-the timed CPU baseline, never as the product.  The product
+`cpu_baseline` / `--impl reference` legs of `bench.py` plus its untimed `parity`
+checker leg (after every timed region: product answers vs this oracle on the tree
+the product exports) -- as the checker or as the timed CPU baseline, never as the
+product.  The product
 (`k8s-device-plugin_b200/` + `libb200dp.so`) must not import, link or execute
 anything under `oracle/`, and it has no CPU fallback for the GPU probe.
 
